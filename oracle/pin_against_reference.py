@@ -1,0 +1,144 @@
+"""Pin the oracle against the reference's own code and write tests/golden/*.npz.
+
+Runs ONLY in the build container (needs the read-only reference tree at /root/reference);
+the fixtures it writes are committed so nothing on the GPU box needs the reference.
+
+    python -m oracle.pin_against_reference            # assert + (re)write fixtures
+
+For every seeded case the reference function (imported unmodified from /root/reference) and the
+oracle restatement are run on the same CPU tensors and compared BIT-FOR-BIT (torch.equal); the
+script aborts on any difference.  Third-party imports the reference needs only at module import
+time (open3d in lib/eval.py:3, MinkowskiEngine in util/transform_estimation.py:2) are stubbed.
+"""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = '/root/reference'
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+
+def _import_reference():
+    for name in ('open3d', 'MinkowskiEngine'):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.path.insert(0, REF)
+    from scripts.SC2_PCR.SC2_PCR import Matcher
+    from scripts.SC2_PCR.common import rigid_transform_3d
+    from scripts.SC2_PCR.utils.SE3 import transform, integrate_trans
+    from lib.eval import find_nn_gpu
+    from lib.metrics import pdist
+    from util.transform_estimation import est_quad_linear_robust
+    sys.path.remove(REF)
+    return dict(Matcher=Matcher, rigid_transform_3d=rigid_transform_3d, transform=transform,
+                integrate_trans=integrate_trans, find_nn_gpu=find_nn_gpu, pdist=pdist,
+                est_quad_linear_robust=est_quad_linear_robust)
+
+
+def _eq(a, b, what):
+    ok = torch.equal(torch.as_tensor(a), torch.as_tensor(b))
+    if not ok:
+        raise SystemExit(f'PIN FAILED: {what}')
+    print(f'  pinned  {what}')
+
+
+def pin_sc2pcr(ref, n, inlier_ratio, seed, cfg_json):
+    from eyoc_b200 import synth
+    from oracle import sc2pcr_oracle as O
+    cfg = O.SC2Config(**{k: cfg_json[k] for k in ('inlier_threshold', 'num_node', 'd_thre', 'num_iterations',
+                                                 'ratio', 'nms_radius', 'max_points', 'k1', 'k2')})
+    m = ref['Matcher'](inlier_threshold=cfg.inlier_threshold, num_node=cfg.num_node, use_mutual=False,
+                       d_thre=cfg.d_thre, num_iterations=cfg.num_iterations, ratio=cfg.ratio,
+                       nms_radius=cfg.nms_radius, max_points=cfg.max_points, k1=cfg.k1, k2=cfg.k2)
+    src, tgt, T_gt, inl = synth.make_correspondences(n, inlier_ratio, seed)
+    src_t, tgt_t = torch.from_numpy(src)[None], torch.from_numpy(tgt)[None]
+    T_ref, fit_ref = m.SC2_PCR(src_t.clone(), tgt_t.clone())
+    det = {}
+    T_or, fit_or = O.sc2_pcr(src_t.clone(), tgt_t.clone(), cfg, det)
+    tag = f'sc2pcr n={n} r={inlier_ratio} seed={seed}'
+    _eq(T_ref, T_or, tag + ' final_trans')
+    _eq(fit_ref, fit_or, tag + ' seedwise_fitness')
+    # stage functions individually
+    src_dist, cross, SC, hard, tight = O.first_order(src_t, tgt_t, cfg)
+    conf_ref = m.cal_leading_eigenvector(SC, method='power')
+    _eq(conf_ref, det['confidence'], tag + ' leading eigenvector')
+    seeds_ref = m.pick_seeds(src_dist, conf_ref, R=cfg.nms_radius, max_num=int(n * cfg.ratio))
+    _eq(seeds_ref, det['seeds'], tag + ' seeds')
+    T0_ref, _ = m.cal_seed_trans(seeds_ref, det['SC2'], src_t, tgt_t)
+    _eq(T0_ref, det['initial_trans'], tag + ' cal_seed_trans')
+    _eq(m.post_refinement(T0_ref, src_t, tgt_t, 20), T_or, tag + ' post_refinement')
+    warp = ref['transform'](src_t, T_ref)
+    labels = (torch.sum((warp - tgt_t) ** 2, dim=-1) ** 0.5 < cfg.inlier_threshold)
+    out = dict(src=src, tgt=tgt, T_gt=T_gt, gt_inlier=inl,
+               confidence=det['confidence'][0].numpy(), global_iters=det['global_iters'],
+               seeds=det['seeds'][0].numpy().astype(np.int32),
+               topk1=det['topk1'][0].numpy().astype(np.int16), topk2=det['topk2'][0].numpy().astype(np.int16),
+               local_iters=det['local_iters'], seed_trans=det['seed_trans'][0].numpy(),
+               fitness=fit_ref[0].numpy(), best_seed=int(det['best_seed'][0]),
+               initial_trans=det['initial_trans'][0].numpy(), refine_counts=np.array(det['refine_counts']),
+               final_trans=T_ref[0].numpy(), labels=labels[0].numpy(),
+               cfg=json.dumps(cfg.__dict__))
+    np.savez_compressed(os.path.join(GOLD, f'sc2pcr_n{n}_s{seed}.npz'), **out)
+
+
+def pin_small(ref):
+    from oracle import sc2pcr_oracle as O, matching_oracle as MO
+    g = torch.Generator().manual_seed(7)
+    # Kabsch, SE3
+    A = torch.randn(5, 20, 3, generator=g) * 10
+    B = torch.randn(5, 20, 3, generator=g) * 10
+    w = torch.rand(5, 20, generator=g)
+    _eq(ref['rigid_transform_3d'](A, B, w.clone()), O.kabsch_weighted(A, B, w.clone()), 'rigid_transform_3d weighted')
+    _eq(ref['rigid_transform_3d'](A, B), O.kabsch_weighted(A, B), 'rigid_transform_3d unweighted')
+    T = O.kabsch_weighted(A, B, w.clone())
+    _eq(ref['transform'](A, T), O.se3_transform(A, T), 'SE3.transform')
+    _eq(ref['integrate_trans'](T[:, :3, :3], T[:, :3, 3:4]), O.se3_integrate(T[:, :3, :3], T[:, :3, 3:4]),
+        'SE3.integrate_trans')
+    # kNN
+    F0 = torch.nn.functional.normalize(torch.randn(1500, 32, generator=g), dim=1)
+    F1 = torch.nn.functional.normalize(torch.randn(1300, 32, generator=g), dim=1)
+    F1[100:140] = F1[200:240]                       # exact duplicates -> first-index ties
+    i_ref, d_ref = ref['find_nn_gpu'](F0, F1, nn_max_n=500, return_distance=True)
+    i_or, d_or = MO.find_nn(F0, F1, nn_max_n=500, return_distance=True)
+    _eq(i_ref, i_or, 'find_nn_gpu indices (chunked)')
+    _eq(d_ref, d_or, 'find_nn_gpu distances')
+    _eq(ref['find_nn_gpu'](F0, F1), MO.find_nn(F0, F1), 'find_nn_gpu indices (unchunked)')
+    _eq(ref['pdist'](F0[:64], F1[:64], 'SquareL2'), MO.pdist_sq(F0[:64], F1[:64]), 'pdist SquareL2')
+    _eq(ref['pdist'](F0[:64], F1[:64], 'L2'), MO.pdist_l2(F0[:64], F1[:64]), 'pdist L2')
+    cos_idx = MO.match_argmin(F0, F1)
+    seq_sq, _ = MO.knn_sq_seq(F0.numpy(), F1.numpy())
+    seq_cos, _ = MO.knn_cos_seq(F0.numpy(), F1.numpy())
+    print('  kernel-order vs torch-order index agreement: sq', float((seq_sq == i_ref.numpy()).mean()),
+          'cos', float((seq_cos == cos_idx.numpy()).mean()))
+    np.savez_compressed(os.path.join(GOLD, 'knn_1500x1300.npz'), F0=F0.numpy(), F1=F1.numpy(),
+                        idx_sq=i_ref.numpy(), dist_sq=d_ref.numpy(), idx_cos=cos_idx.numpy())
+    # IRLS
+    p0 = torch.randn(400, 3, generator=g) * 5
+    Tq = O.kabsch_weighted(A[:1], B[:1])[0]
+    p1 = p0 @ torch.linalg.qr(torch.randn(3, 3, generator=g))[0].T * 0 + p0 + torch.tensor([0.3, -0.2, 0.1]) \
+        + 0.01 * torch.randn(400, 3, generator=g)
+    T_ref = ref['est_quad_linear_robust'](p0, p1)
+    _eq(T_ref, MO.irls_pose(p0, p1), 'est_quad_linear_robust')
+    np.savez_compressed(os.path.join(GOLD, 'irls_400.npz'), p0=p0.numpy(), p1=p1.numpy(), T=T_ref.numpy())
+    np.savez_compressed(os.path.join(GOLD, 'kabsch_5x20.npz'), A=A.numpy(), B=B.numpy(), w=w.numpy(),
+                        T=O.kabsch_weighted(A, B, w.clone()).numpy())
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    ref = _import_reference()
+    sys.path.insert(0, ROOT)
+    cfg_json = json.load(open(os.path.join(REF, 'scripts/SC2_PCR/config_json/config_KITTI.json')))
+    pin_small(ref)
+    for n, r, seed in ((1000, 0.3, 1), (2000, 0.15, 2), (2000, 0.5, 3), (25, 0.6, 4), (8000, 0.2, 5)):
+        pin_sc2pcr(ref, n, r, seed, cfg_json)
+    print('ALL PINNED')
+
+
+if __name__ == '__main__':
+    main()
