@@ -1,0 +1,73 @@
+"""ctypes binding of libeyoc_b200.so (the C-ABI boundary, include/eyoc_b200.h).
+
+There is NO fallback: if the shared library is missing or a CUDA device is not present the
+product path raises.  The oracle under ``oracle/`` is never imported from here.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libeyoc_b200.so')
+
+c_void_p, c_int, c_int64, c_size_t, c_float = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
+                                                ctypes.c_size_t, ctypes.c_float)
+
+
+class SC2Cfg(ctypes.Structure):
+    """struct eyoc_sc2_cfg (include/eyoc_b200.h)."""
+    _fields_ = [('inlier_threshold', c_float), ('d_thre', c_float), ('ratio', c_float), ('nms_radius', c_float),
+                ('num_iterations', c_int), ('k1', c_int), ('k2', c_int), ('refine_iterations', c_int)]
+
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library; fail loudly when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} not built: run `python -m eyoc_b200.csrc.build` (nvcc, sm_100a). '
+                'eyoc_b200 has no CPU or PyTorch fallback.')
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.eyoc_last_error.restype = ctypes.c_char_p
+        _lib.eyoc_version.restype = c_int
+        for name in dir(_lib):
+            pass
+        for name in ('eyoc_knn1_workspace_bytes', 'eyoc_sc2pcr_workspace_bytes', 'eyoc_coordmap_workspace_bytes'):
+            if hasattr(_lib, name):
+                getattr(_lib, name).restype = c_size_t
+    return _lib
+
+
+def check(code):
+    if code != 0:
+        raise RuntimeError(f'eyoc_b200 C-ABI error {code}: {lib().eyoc_last_error().decode()}')
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (or NULL for None)."""
+    if t is None:
+        return c_void_p(0)
+    if not t.is_cuda:
+        raise RuntimeError('eyoc_b200 kernels need CUDA tensors (no CPU fallback)')
+    if not t.is_contiguous():
+        raise RuntimeError('eyoc_b200 kernels need contiguous tensors')
+    return c_void_p(t.data_ptr())
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('eyoc_b200: tensor is on %s; the B200 path has no CPU fallback' % t.device)
+
+
+def f32c(t):
+    return t.detach().to(torch.float32).contiguous()
