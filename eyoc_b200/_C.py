@@ -16,9 +16,24 @@ c_void_p, c_int, c_int64, c_size_t, c_float = (ctypes.c_void_p, ctypes.c_int, ct
 
 
 class SC2Cfg(ctypes.Structure):
-    """struct eyoc_sc2_cfg (include/eyoc_b200.h)."""
-    _fields_ = [('inlier_threshold', c_float), ('d_thre', c_float), ('ratio', c_float), ('nms_radius', c_float),
-                ('num_iterations', c_int), ('k1', c_int), ('k2', c_int), ('refine_iterations', c_int)]
+    """struct eyoc_sc2_cfg (include/eyoc_b200.h).  c_float rounds Python doubles to fp32 exactly like torch
+    rounds a Python scalar that meets an fp32 tensor."""
+    _fields_ = [('inlier_threshold', c_float), ('d_thre', c_float), ('d_thre_half', c_float), ('d_thre_sq', c_float),
+                ('nms_radius', c_float), ('refine_threshold', c_float), ('num_iterations', c_int), ('k1', c_int),
+                ('k2', c_int), ('refine_iterations', c_int)]
+
+
+class SC2Hooks(ctypes.Structure):
+    """struct eyoc_sc2_hooks."""
+    _fields_ = [('confidence', c_void_p), ('seeds', c_void_p), ('initial_trans', c_void_p)]
+
+
+class SC2Layout(ctypes.Structure):
+    """struct eyoc_sc2_layout."""
+    _fields_ = [(k, c_size_t) for k in ('points', 'hard_bits', 'tight_bits', 'vbuf', 'u', 'confidence', 'scores', 'seeds',
+                                        'topk1', 'topk2', 'local_v', 'seed_weights', 'seed_trans', 'counters',
+                                        'global_iters', 'local_notclose', 'best_seed', 'refine_counts', 'total')] + \
+               [(k, c_int) for k in ('words_per_row', 'k1', 'k2', 'num_seeds')]
 
 
 _lib = None
@@ -35,8 +50,6 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.eyoc_last_error.restype = ctypes.c_char_p
         _lib.eyoc_version.restype = c_int
-        for name in dir(_lib):
-            pass
         for name in ('eyoc_knn1_workspace_bytes', 'eyoc_sc2pcr_workspace_bytes', 'eyoc_coordmap_workspace_bytes'):
             if hasattr(_lib, name):
                 getattr(_lib, name).restype = c_size_t

@@ -1,0 +1,282 @@
+// Coordinate maps and kernel maps for generalized sparse convolution (sm_100a).
+//
+// Replaces what MinkowskiEngine's coordinate manager does underneath the reference's
+// ME.SparseTensor(F, coordinates=C) (scripts/test_kitti.py:143-147) and every
+// ME.MinkowskiConvolution / MinkowskiConvolutionTranspose in model/resunet.py:31-140:
+//   * an open-addressing hash of the (batch, x, y, z) int32 coordinates (64-bit packed key -> row index),
+//   * the stride-2 coordinate sets  unique(floor(c / 2ts) * 2ts)  in first-occurrence order,
+//   * neighbour tables  nbr[k, o] = row of  c_o + off_k * step  in the input map (or -1),
+//     off_k enumerating {-r..r}^3 with x fastest (k = ix + K*(iy + K*iz)).
+// All of it is integer work bounded by HBM/L2 latency; lookups are one probe sequence per (k, o) with
+// coalesced writes along o.
+#include "common.cuh"
+#include "../../include/eyoc_b200.h"
+
+namespace {
+
+constexpr unsigned long long EMPTY = 0xffffffffffffffffull;
+
+__device__ __forceinline__ bool in_range16(int v) { return v >= -32768 && v <= 32767; }
+
+__device__ __forceinline__ unsigned long long pack4(int b, int x, int y, int z) {
+    return ((unsigned long long)(unsigned int)(b & 0xffff) << 48) | ((unsigned long long)(unsigned int)((x + 32768) & 0xffff) << 32) |
+           ((unsigned long long)(unsigned int)((y + 32768) & 0xffff) << 16) | (unsigned long long)(unsigned int)((z + 32768) & 0xffff);
+}
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return k;
+}
+
+// insert key; value = min(row) over duplicates.  Returns the slot.
+__device__ __forceinline__ long long hash_insert_min(unsigned long long* keys, int* vals, long long cap, unsigned long long key, int row) {
+    long long slot = (long long)(mix64(key) & (unsigned long long)(cap - 1));
+    while (true) {
+        const unsigned long long prev = atomicCAS(keys + slot, EMPTY, key);
+        if (prev == EMPTY || prev == key) {
+            atomicMin(vals + slot, row);
+            return slot;
+        }
+        slot = (slot + 1) & (cap - 1);
+    }
+}
+
+__device__ __forceinline__ int hash_lookup(const unsigned long long* __restrict__ keys, const int* __restrict__ vals, long long cap,
+                                           unsigned long long key) {
+    long long slot = (long long)(mix64(key) & (unsigned long long)(cap - 1));
+    while (true) {
+        const unsigned long long k = keys[slot];
+        if (k == key) return vals[slot];
+        if (k == EMPTY) return -1;
+        slot = (slot + 1) & (cap - 1);
+    }
+}
+
+__global__ void hash_clear_kernel(unsigned long long* keys, int* vals, long long cap) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) { keys[i] = EMPTY; vals[i] = 0x7fffffff; }
+}
+
+// status[0] |= 1: coordinate out of the 16-bit packed range; |= 2: duplicate coordinate
+__global__ void hash_build_kernel(const int* __restrict__ coords, int n, unsigned long long* keys, int* vals, long long cap,
+                                  int* status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 c = reinterpret_cast<const int4*>(coords)[i];
+    if (!(c.x >= 0 && c.x <= 65535 && in_range16(c.y) && in_range16(c.z) && in_range16(c.w))) { atomicOr(status, 1); return; }
+    hash_insert_min(keys, vals, cap, pack4(c.x, c.y, c.z, c.w), i);
+}
+
+__global__ void hash_check_unique_kernel(const int* __restrict__ coords, int n, const unsigned long long* keys, const int* vals,
+                                         long long cap, int* status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 c = reinterpret_cast<const int4*>(coords)[i];
+    if (hash_lookup(keys, vals, cap, pack4(c.x, c.y, c.z, c.w)) != i) atomicOr(status, 2);
+}
+
+__device__ __forceinline__ int floor_to(int v, int ts) {   // floor(v / ts) * ts for negative v too
+    int q = v / ts;
+    if ((v % ts) != 0 && v < 0) --q;
+    return q * ts;
+}
+
+// pass 1 of the stride-2 coordinate set: coarse key -> min fine row
+__global__ void down_insert_kernel(const int* __restrict__ coords, int n, int ts_out, unsigned long long* keys, int* vals, long long cap) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 c = reinterpret_cast<const int4*>(coords)[i];
+    hash_insert_min(keys, vals, cap, pack4(c.x, floor_to(c.y, ts_out), floor_to(c.z, ts_out), floor_to(c.w, ts_out)), i);
+}
+
+// pass 2: flag first occurrences
+__global__ void down_flag_kernel(const int* __restrict__ coords, int n, int ts_out, const unsigned long long* keys, const int* vals,
+                                 long long cap, int* __restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 c = reinterpret_cast<const int4*>(coords)[i];
+    const unsigned long long key = pack4(c.x, floor_to(c.y, ts_out), floor_to(c.z, ts_out), floor_to(c.w, ts_out));
+    flag[i] = hash_lookup(keys, vals, cap, key) == i ? 1 : 0;
+}
+
+// ---- exclusive scan (three small kernels; n is a few million at most)
+constexpr int SCAN_B = 1024;
+__global__ void scan_block_kernel(const int* __restrict__ in, int n, int* __restrict__ out, int* __restrict__ block_sums) {
+    __shared__ int wsum[32];
+    const int i = blockIdx.x * SCAN_B + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int v = i < n ? in[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int s = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += y;
+        }
+        wsum[lane] = s;
+    }
+    __syncthreads();
+    const int base = warp > 0 ? wsum[warp - 1] : 0;
+    if (i < n) out[i] = base + x - v;
+    if (threadIdx.x == SCAN_B - 1) block_sums[blockIdx.x] = base + x;
+}
+__global__ void scan_sums_kernel(int* block_sums, int nblocks, int* total) {   // single CTA, sequential over chunks
+    __shared__ int carry;
+    __shared__ int wsum[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c0 = 0; c0 < nblocks; c0 += 1024) {
+        const int i = c0 + threadIdx.x;
+        const int v = i < nblocks ? block_sums[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int s = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += y;
+            }
+            wsum[lane] = s;
+        }
+        __syncthreads();
+        const int base = carry + (warp > 0 ? wsum[warp - 1] : 0);
+        if (i < nblocks) block_sums[i] = base + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = base + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+// pass 3: emit coarse coordinates in first-occurrence order and point the hash at the coarse row
+__global__ void down_emit_kernel(const int* __restrict__ coords, int n, int ts_out, const int* __restrict__ flag,
+                                 const int* __restrict__ pos, const int* __restrict__ block_sums, unsigned long long* keys, int* vals,
+                                 long long cap, int* __restrict__ coords_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flag[i]) return;
+    const int4 c = reinterpret_cast<const int4*>(coords)[i];
+    const int4 cc = make_int4(c.x, floor_to(c.y, ts_out), floor_to(c.z, ts_out), floor_to(c.w, ts_out));
+    const int row = pos[i] + block_sums[i / SCAN_B];
+    reinterpret_cast<int4*>(coords_out)[row] = cc;
+    const unsigned long long key = pack4(cc.x, cc.y, cc.z, cc.w);
+    long long slot = (long long)(mix64(key) & (unsigned long long)(cap - 1));
+    while (keys[slot] != key) slot = (slot + 1) & (cap - 1);
+    vals[slot] = row;
+}
+
+// nbr[k, o] = row in the input map of  c_o + off_k * step
+__global__ void kernel_map_kernel(const int* __restrict__ out_coords, int n_out, const unsigned long long* __restrict__ keys,
+                                  const int* __restrict__ vals, long long cap, int ksize, int step, int* __restrict__ nbr) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (o >= n_out) return;
+    const int r = (ksize - 1) / 2;
+    const int ix = k % ksize - r, iy = (k / ksize) % ksize - r, iz = k / (ksize * ksize) - r;
+    const int4 c = reinterpret_cast<const int4*>(out_coords)[o];
+    const int x = c.y + ix * step, y = c.z + iy * step, z = c.w + iz * step;
+    int v = -1;
+    if (in_range16(x) && in_range16(y) && in_range16(z)) v = hash_lookup(keys, vals, cap, pack4(c.x, x, y, z));
+    nbr[(size_t)k * n_out + o] = v;
+}
+
+// rows of one map grouped by the parity class of (x, y, z) / ts  (8 classes): perm sorted by class,
+// used to make the valid kernel offsets of a transposed stride-2 convolution CTA-uniform.
+__global__ void parity_class_kernel(const int* __restrict__ coords, int n, int ts, int* __restrict__ cls) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 c = reinterpret_cast<const int4*>(coords)[i];
+    cls[i] = (((c.y / ts) & 1)) | (((c.z / ts) & 1) << 1) | (((c.w / ts) & 1) << 2);
+}
+
+}  // namespace
+
+extern "C" int eyoc_hash_build(const int32_t* coords, int64_t n, uint64_t* table_keys, int32_t* table_vals, int64_t capacity,
+                               int32_t* status, cudaStream_t stream) {
+    EYOC_CHECK_ARG(coords && table_keys && table_vals && status, "eyoc_hash_build: null argument");
+    EYOC_CHECK_ARG(n >= 0 && n < (1ll << 31), "eyoc_hash_build: bad n");
+    EYOC_CHECK_ARG(capacity >= 2 * n && capacity >= 2 && (capacity & (capacity - 1)) == 0, "eyoc_hash_build: capacity must be a power of two >= 2n");
+    hash_clear_kernel<<<(unsigned)((capacity + 255) / 256), 256, 0, stream>>>((unsigned long long*)table_keys, table_vals, capacity);
+    EYOC_LAUNCH_CHECK();
+    if (n == 0) return EYOC_OK;
+    const unsigned g = (unsigned)((n + 255) / 256);
+    hash_build_kernel<<<g, 256, 0, stream>>>(coords, (int)n, (unsigned long long*)table_keys, table_vals, capacity, status);
+    EYOC_LAUNCH_CHECK();
+    hash_check_unique_kernel<<<g, 256, 0, stream>>>(coords, (int)n, (const unsigned long long*)table_keys, table_vals, capacity, status);
+    EYOC_LAUNCH_CHECK();
+    return EYOC_OK;
+}
+
+extern "C" size_t eyoc_downsample_workspace_bytes(int64_t n) {
+    const size_t nb = (size_t)((n + SCAN_B - 1) / SCAN_B);
+    return eyoc_align((size_t)n * 4) * 2 + eyoc_align((nb + 1) * 4);
+}
+
+extern "C" int eyoc_coords_downsample(const int32_t* coords, int64_t n, int ts_out, uint64_t* table_keys, int32_t* table_vals,
+                                      int64_t capacity, int32_t* coords_out, int32_t* n_out, void* workspace, size_t workspace_bytes,
+                                      cudaStream_t stream) {
+    EYOC_CHECK_ARG(coords && table_keys && table_vals && coords_out && n_out, "eyoc_coords_downsample: null argument");
+    EYOC_CHECK_ARG(n >= 0 && n < (1ll << 31) && ts_out >= 2, "eyoc_coords_downsample: bad n / stride");
+    EYOC_CHECK_ARG(capacity >= 2 * n && capacity >= 2 && (capacity & (capacity - 1)) == 0, "eyoc_coords_downsample: capacity must be a power of two >= 2n");
+    if (workspace == nullptr || workspace_bytes < eyoc_downsample_workspace_bytes(n)) {
+        eyoc_set_error("eyoc_coords_downsample: workspace too small");
+        return EYOC_ERR_WORKSPACE;
+    }
+    hash_clear_kernel<<<(unsigned)((capacity + 255) / 256), 256, 0, stream>>>((unsigned long long*)table_keys, table_vals, capacity);
+    EYOC_LAUNCH_CHECK();
+    if (n == 0) { EYOC_CUDA(cudaMemsetAsync(n_out, 0, 4, stream)); return EYOC_OK; }
+    WsCarver c(workspace, workspace_bytes);
+    int* flag = c.take<int>(n);
+    int* pos = c.take<int>(n);
+    const int nb = (int)((n + SCAN_B - 1) / SCAN_B);
+    int* sums = c.take<int>(nb + 1);
+    const unsigned g = (unsigned)((n + 255) / 256);
+    down_insert_kernel<<<g, 256, 0, stream>>>(coords, (int)n, ts_out, (unsigned long long*)table_keys, table_vals, capacity);
+    EYOC_LAUNCH_CHECK();
+    down_flag_kernel<<<g, 256, 0, stream>>>(coords, (int)n, ts_out, (const unsigned long long*)table_keys, table_vals, capacity, flag);
+    EYOC_LAUNCH_CHECK();
+    scan_block_kernel<<<nb, SCAN_B, 0, stream>>>(flag, (int)n, pos, sums);
+    EYOC_LAUNCH_CHECK();
+    scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, nb, n_out);
+    EYOC_LAUNCH_CHECK();
+    down_emit_kernel<<<g, 256, 0, stream>>>(coords, (int)n, ts_out, flag, pos, sums, (unsigned long long*)table_keys, table_vals, capacity,
+                                            coords_out);
+    EYOC_LAUNCH_CHECK();
+    return EYOC_OK;
+}
+
+extern "C" int eyoc_kernel_map(const int32_t* out_coords, int64_t n_out, const uint64_t* in_table_keys, const int32_t* in_table_vals,
+                               int64_t capacity, int ksize, int step, int32_t* nbr, cudaStream_t stream) {
+    EYOC_CHECK_ARG(out_coords && in_table_keys && in_table_vals && nbr, "eyoc_kernel_map: null argument");
+    EYOC_CHECK_ARG(ksize >= 1 && (ksize & 1) && ksize <= 7, "eyoc_kernel_map: kernel size must be odd and <= 7 (got %d)", ksize);
+    EYOC_CHECK_ARG(n_out >= 0 && n_out < (1ll << 31), "eyoc_kernel_map: bad n_out");
+    if (n_out == 0) return EYOC_OK;
+    dim3 grid((unsigned)((n_out + 255) / 256), ksize * ksize * ksize);
+    kernel_map_kernel<<<grid, 256, 0, stream>>>(out_coords, (int)n_out, (const unsigned long long*)in_table_keys, in_table_vals, capacity,
+                                                ksize, step, nbr);
+    EYOC_LAUNCH_CHECK();
+    return EYOC_OK;
+}
+
+extern "C" int eyoc_parity_class(const int32_t* coords, int64_t n, int ts, int32_t* cls, cudaStream_t stream) {
+    EYOC_CHECK_ARG(coords && cls && ts >= 1, "eyoc_parity_class: bad argument");
+    if (n == 0) return EYOC_OK;
+    parity_class_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(coords, (int)n, ts, cls);
+    EYOC_LAUNCH_CHECK();
+    return EYOC_OK;
+}

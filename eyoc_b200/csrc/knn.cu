@@ -13,6 +13,7 @@
 // "smallest value, then smallest index" exactly.  Accumulation order is fixed: one fp32 FMA per
 // descriptor channel, channels ascending (oracle/matching_oracle.py knn_*_seq restates it).
 #include "common.cuh"
+#include "../../include/eyoc_b200.h"
 
 namespace {
 

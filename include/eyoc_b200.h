@@ -1,0 +1,93 @@
+/* eyoc_b200 — C ABI of the B200-native EYOC registration-inference hot path.
+ *
+ * The reference (liuQuan98/EYOC) has no FFI on this path: everything is Python calling
+ * MinkowskiEngine's pybind backend and torch ATen.  This header is therefore the boundary a
+ * maintainer binds INSTEAD of those two libraries (ctypes stub: eyoc_b200/_C.py; see
+ * INTEGRATION.md).  Each entry point cites the reference interface it replaces
+ * (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - return 0 = OK; -1 bad argument; -2 CUDA error; -3 workspace too small; -4 degenerate input.
+ *     eyoc_last_error() returns a thread-local message for the last non-zero return.
+ *   - every tensor pointer is CALLER-OWNED DEVICE memory, contiguous row-major; the library
+ *     never allocates, frees or retains device memory: scratch comes from the caller through
+ *     (workspace, workspace_bytes) sized by the matching *_workspace_bytes() function.
+ *   - all work is stream-ordered on `stream`; no call synchronises the device or the host.
+ *   - no torch / C++ types cross the boundary.
+ */
+#ifndef EYOC_B200_H
+#define EYOC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* eyoc_stream_t; /* == cudaStream_t */
+
+int eyoc_version(void);
+const char* eyoc_last_error(void);
+int eyoc_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------- nearest neighbour matching
+ * Replaces lib/eval.py:18-48 find_nn_gpu (+ lib/metrics.py:26-27 pdist 'SquareL2')  [form 0]
+ * and the matching core of scripts/SC2_PCR/SC2_PCR.py:296-298 Matcher.match_pair       [form 1].
+ * q [batch, nq, dim], r [batch, nr, dim] fp32 -> idx [batch, nq] int64 (ties -> lowest index,
+ * NaN distance wins like torch.argmin), dist [batch, nq] fp32 (either output may be NULL). */
+size_t eyoc_knn1_workspace_bytes(int batch, int64_t nq);
+int eyoc_knn1(const float* q, const float* r, int batch, int64_t nq, int64_t nr, int dim, int form,
+              void* workspace, size_t workspace_bytes, int64_t* idx, float* dist, eyoc_stream_t stream);
+
+/* ---------------------------------------------------------------- SC2-PCR estimator
+ * Replaces scripts/SC2_PCR/SC2_PCR.py:307-384 Matcher.SC2_PCR (first/second-order spatial
+ * compatibility, :170-196 power iteration, :33-59 pick_seeds, :61-168 cal_seed_trans,
+ * :238-278 post_refinement), the label pass of :409-411 Matcher.estimator, and
+ * scripts/SC2_PCR/common.py:7-45 rigid_transform_3d (weighted Kabsch; 3x3 SVD on device).
+ * Batched over `batch` independent pairs (the reference asserts batch == 1, SC2_PCR.py:44,249).
+ * Thresholds are passed already rounded to fp32 exactly as torch rounds Python scalars. */
+typedef struct {
+    float inlier_threshold;  /* config_KITTI.json:6   final labels + per-seed fitness            */
+    float d_thre;            /* :7  first-order compatibility   cross < d_thre                    */
+    float d_thre_half;       /* fp32(d_thre / 2)  tight compatibility, SC2_PCR.py:357             */
+    float d_thre_sq;         /* fp32(d_thre ** 2) soft measure denominator, SC2_PCR.py:341        */
+    float nms_radius;        /* :14 */
+    float refine_threshold;  /* 1.2 unless inlier_threshold == 0.10, SC2_PCR.py:254-257           */
+    int num_iterations;      /* :2  power-iteration cap                                           */
+    int k1, k2;              /* :4-5 (the k1 > n fallback to 4/4, SC2_PCR.py:76-78, is applied inside) */
+    int refine_iterations;   /* 20, SC2_PCR.py:374 */
+} eyoc_sc2_cfg;
+
+/* Optional stage inputs: when non-NULL the corresponding stage is skipped and these device arrays are
+ * used instead (stage-parity tests feed the oracle's upstream tensors through them). */
+typedef struct {
+    const float* confidence;      /* [batch, n]      skip the leading-eigenvector stage        */
+    const int32_t* seeds;         /* [batch, S]      skip NMS + ranking                        */
+    const float* initial_trans;   /* [batch, 4, 4]   skip the whole seed stage                 */
+} eyoc_sc2_hooks;
+
+/* Byte offsets of the intermediate buffers inside the workspace (for tests and diagnostics). */
+typedef struct {
+    size_t points, hard_bits, tight_bits, vbuf, u, confidence, scores, seeds, topk1, topk2, local_v,
+        seed_weights, seed_trans, counters, global_iters, local_notclose, best_seed, refine_counts, total;
+    int words_per_row, k1, k2, num_seeds;
+} eyoc_sc2_layout;
+
+int eyoc_sc2pcr_layout(int batch, int n, int num_seeds, const eyoc_sc2_cfg* cfg, eyoc_sc2_layout* out);
+size_t eyoc_sc2pcr_workspace_bytes(int batch, int n, int num_seeds, const eyoc_sc2_cfg* cfg);
+/* src, tgt [batch, n, 3] fp32 putative correspondences  ->
+ * trans [batch, 4, 4], fitness [batch, num_seeds] (may be NULL), labels [batch, n] fp32 0/1 (may be NULL). */
+int eyoc_sc2pcr(const float* src, const float* tgt, int batch, int n, int num_seeds, const eyoc_sc2_cfg* cfg,
+                const eyoc_sc2_hooks* hooks, void* workspace, size_t workspace_bytes, float* trans, float* fitness,
+                float* labels, eyoc_stream_t stream);
+
+/* scripts/SC2_PCR/common.py:7-45 rigid_transform_3d: A, B [batch, n, 3], w [batch, n] (NULL = ones;
+ * negative weights are zeroed IN PLACE like common.py:20) -> T [batch, 4, 4]. */
+int eyoc_kabsch_batched(const float* A, const float* B, float* w, int batch, int n, float weight_threshold,
+                        float* T, eyoc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EYOC_B200_H */

@@ -73,6 +73,16 @@ def pin_sc2pcr(ref, n, inlier_ratio, seed, cfg_json):
     _eq(m.post_refinement(T0_ref, src_t, tgt_t, 20), T_or, tag + ' post_refinement')
     warp = ref['transform'](src_t, T_ref)
     labels = (torch.sum((warp - tgt_t) ** 2, dim=-1) ** 0.5 < cfg.inlier_threshold)
+    # second oracle mode: stable tie rule (what the CUDA path implements; SC2Config.stable_ties docstring)
+    import dataclasses
+    cfg_s = dataclasses.replace(cfg, stable_ties=True)
+    ds = {}
+    T_st, fit_st = O.sc2_pcr(src_t.clone(), tgt_t.clone(), cfg_s, ds)
+    labels_st = (torch.sum((O.se3_transform(src_t, T_st) - tgt_t) ** 2, dim=-1) ** 0.5 < cfg.inlier_threshold)
+    same_seed = (ds['seeds'] == det['seeds'])[0]
+    print(f'  stable-vs-reference tie rule: seeds equal {float(same_seed.float().mean()):.4f}, '
+          f'topk1 rows equal {float((ds["topk1"] == det["topk1"]).all(-1).float().mean()):.4f}, '
+          f'|dT| {float((T_st - T_ref).abs().max()):.2e}, label hamming {int((labels_st != labels).sum())}')
     out = dict(src=src, tgt=tgt, T_gt=T_gt, gt_inlier=inl,
                confidence=det['confidence'][0].numpy(), global_iters=det['global_iters'],
                seeds=det['seeds'][0].numpy().astype(np.int32),
@@ -81,6 +91,12 @@ def pin_sc2pcr(ref, n, inlier_ratio, seed, cfg_json):
                fitness=fit_ref[0].numpy(), best_seed=int(det['best_seed'][0]),
                initial_trans=det['initial_trans'][0].numpy(), refine_counts=np.array(det['refine_counts']),
                final_trans=T_ref[0].numpy(), labels=labels[0].numpy(),
+               st_seeds=ds['seeds'][0].numpy().astype(np.int32), st_topk1=ds['topk1'][0].numpy().astype(np.int16),
+               st_topk2=ds['topk2'][0].numpy().astype(np.int16), st_local_iters=ds['local_iters'],
+               st_seed_weights=ds['seed_weights'][0].numpy(), st_seed_trans=ds['seed_trans'][0].numpy(),
+               st_fitness=fit_st[0].numpy(), st_best_seed=int(ds['best_seed'][0]),
+               st_initial_trans=ds['initial_trans'][0].numpy(), st_refine_counts=np.array(ds['refine_counts']),
+               st_final_trans=T_st[0].numpy(), st_labels=labels_st[0].numpy(),
                cfg=json.dumps(cfg.__dict__))
     np.savez_compressed(os.path.join(GOLD, f'sc2pcr_n{n}_s{seed}.npz'), **out)
 

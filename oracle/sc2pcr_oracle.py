@@ -28,6 +28,12 @@ class SC2Config:
     max_points: int = 8000
     k1: int = 30
     k2: int = 20
+    # Tie rule of the three argsort(descending=True) calls (SC2_PCR.py:53,84,105).  False = exactly what
+    # the reference issues (stable unspecified): torch-CPU then orders ties by its AVX-512 quicksort, which
+    # is deterministic but not index-ordered (measured: 0.03 % agreement with a stable sort on 8000 integer
+    # scores) - this is the mode pinned bit-for-bit against the reference.  True = 'descending value, lowest
+    # index first', the rule the CUDA path implements (and what torch-CUDA's radix sort yields).
+    stable_ties: bool = False
 
 
 # --------------------------------------------------------------------------- SE3
@@ -114,13 +120,13 @@ def first_order(src, tgt, cfg):
     return src_dist, cross, SC, hard, tight
 
 
-def pick_seeds(dists, scores, R, max_num):
+def pick_seeds(dists, scores, R, max_num, stable=False):
     """SC2_PCR.py:33-59 (bs = 1)."""
     assert scores.shape[0] == 1
     rel = scores.T >= scores
     rel = rel.bool() | (dists[0] >= R).bool()
     is_local_max = rel.min(-1)[0].float()
-    order = torch.argsort(scores * is_local_max, dim=1, descending=True)
+    order = torch.argsort(scores * is_local_max, dim=1, descending=True, stable=stable)
     return order[:, 0:max_num].detach()
 
 
@@ -131,7 +137,7 @@ def seed_stage(seeds, SC2, src, tgt, cfg, detail=None):
     k1, k2 = cfg.k1, cfg.k2
     if k1 > num_channels:                                             # :76-78
         k1 = k2 = 4
-    knn_idx = torch.argsort(SC2, dim=2, descending=True)[:, :, 0:k1]  # :84-85
+    knn_idx = torch.argsort(SC2, dim=2, descending=True, stable=cfg.stable_ties)[:, :, 0:k1]  # :84-85
     flat = knn_idx.contiguous().view([bs, -1])[:, :, None].expand(-1, -1, 3)
     src_knn = src.gather(dim=1, index=flat).view([bs, -1, k1, 3])
     tgt_knn = tgt.gather(dim=1, index=flat).view([bs, -1, k1, 3])
@@ -139,7 +145,7 @@ def seed_stage(seeds, SC2, src, tgt, cfg, detail=None):
     td = ((tgt_knn[:, :, :, None, :] - tgt_knn[:, :, None, :, :]) ** 2).sum(-1) ** 0.5
     local_hard = (torch.abs(sd - td) < cfg.d_thre).float()            # :99
     local_sc2 = torch.matmul(local_hard[:, :, :1, :], local_hard)     # :100
-    fine = torch.argsort(local_sc2, dim=3, descending=True)[:, :, :, 0:k2]   # :105-106
+    fine = torch.argsort(local_sc2, dim=3, descending=True, stable=cfg.stable_ties)[:, :, :, 0:k2]   # :105-106
     num = fine.shape[1]
     fine_e = fine.contiguous().view([bs, num, -1])[:, :, :, None].expand(-1, -1, -1, 3)
     src_f = src_knn.gather(dim=2, index=fine_e).view([bs, -1, k2, 3])
@@ -203,7 +209,7 @@ def sc2_pcr(src, tgt, cfg, detail=None, dense_weight=True):
         src, tgt, num_corr = src[:, :cfg.max_points], tgt[:, :cfg.max_points], cfg.max_points
     src_dist, cross, SC, hard, tight = first_order(src, tgt, cfg)
     conf, it0 = power_iteration(SC, cfg.num_iterations)               # :349
-    seeds = pick_seeds(src_dist, conf, cfg.nms_radius, int(num_corr * cfg.ratio))   # :350
+    seeds = pick_seeds(src_dist, conf, cfg.nms_radius, int(num_corr * cfg.ratio), cfg.stable_ties)   # :350
     s_hard = hard.gather(1, seeds[:, :, None].expand(-1, -1, num_corr))
     s_tight = tight.gather(1, seeds[:, :, None].expand(-1, -1, num_corr))
     SC2 = torch.matmul(s_tight, tight) * s_hard                       # :363
