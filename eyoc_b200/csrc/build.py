@@ -50,7 +50,8 @@ def build(force=False, verbose=False):
         list(ex.map(compile_one, jobs))
     objs = [os.path.join(objdir, s.replace('.cu', '.o')) for s in srcs]
     if force or jobs or _stale(LIB, objs):
-        r = subprocess.run([NVCC, '-shared', '-o', LIB, *objs, '-lcudart'], capture_output=True, text=True)
+        r = subprocess.run([NVCC, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', LIB, *objs, '-lcudart'],
+                           capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')
     return LIB

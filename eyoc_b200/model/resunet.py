@@ -1,0 +1,119 @@
+"""FCGF ResUNet feature extractor with the reference's model/resunet.py interface, on sm_100a kernels.
+
+``ResUNet2`` mirrors model/resunet.py:10-193 (same constructor, same sub-module names, MinkowskiEngine
+state-dict keys), and ``ResUNetBN2C`` (:206-209) is the default model of the reference (config.py:82).
+``forward`` issues 23 fused launches (conv + folded BN + residual + ReLU, skip concatenation read in
+place, final L2 normalisation in the last epilogue) instead of ~90 separate MinkowskiEngine / torch ops.
+"""
+import torch
+import torch.nn as nn
+
+from ..nn import MinkowskiConvolution, MinkowskiConvolutionTranspose, conv_bn_act
+from ..sparse import SparseTensor
+from .common import get_norm
+from .residual_block import get_block
+
+
+class ResUNet2(nn.Module):
+    NORM_TYPE = None
+    BLOCK_NORM_TYPE = 'BN'
+    CHANNELS = [None, 32, 64, 128, 256]
+    TR_CHANNELS = [None, 32, 64, 64, 128]
+
+    def __init__(self, in_channels=3, out_channels=32, bn_momentum=0.1, normalize_feature=None, conv1_kernel_size=None,
+                 D=3):
+        super().__init__()
+        self.D = D
+        NORM_TYPE, BLOCK_NORM_TYPE = self.NORM_TYPE, self.BLOCK_NORM_TYPE
+        CHANNELS, TR_CHANNELS = self.CHANNELS, self.TR_CHANNELS
+        self.normalize_feature = normalize_feature
+
+        def conv(cin, cout, k, stride=1, bias=False):
+            return MinkowskiConvolution(cin, cout, kernel_size=k, stride=stride, dilation=1, bias=bias, dimension=D)
+
+        def conv_tr(cin, cout):
+            return MinkowskiConvolutionTranspose(cin, cout, kernel_size=3, stride=2, dilation=1, bias=False, dimension=D)
+
+        def norm(c):
+            return get_norm(NORM_TYPE, c, bn_momentum=bn_momentum, D=D)
+
+        def block(c):
+            return get_block(BLOCK_NORM_TYPE, c, c, bn_momentum=bn_momentum, D=D)
+
+        self.conv1 = conv(in_channels, CHANNELS[1], conv1_kernel_size)
+        self.norm1 = norm(CHANNELS[1])
+        self.block1 = block(CHANNELS[1])
+        self.conv2 = conv(CHANNELS[1], CHANNELS[2], 3, stride=2)
+        self.norm2 = norm(CHANNELS[2])
+        self.block2 = block(CHANNELS[2])
+        self.conv3 = conv(CHANNELS[2], CHANNELS[3], 3, stride=2)
+        self.norm3 = norm(CHANNELS[3])
+        self.block3 = block(CHANNELS[3])
+        self.conv4 = conv(CHANNELS[3], CHANNELS[4], 3, stride=2)
+        self.norm4 = norm(CHANNELS[4])
+        self.block4 = block(CHANNELS[4])
+        self.conv4_tr = conv_tr(CHANNELS[4], TR_CHANNELS[4])
+        self.norm4_tr = norm(TR_CHANNELS[4])
+        self.block4_tr = block(TR_CHANNELS[4])
+        self.conv3_tr = conv_tr(CHANNELS[3] + TR_CHANNELS[4], TR_CHANNELS[3])
+        self.norm3_tr = norm(TR_CHANNELS[3])
+        self.block3_tr = block(TR_CHANNELS[3])
+        self.conv2_tr = conv_tr(CHANNELS[2] + TR_CHANNELS[3], TR_CHANNELS[2])
+        self.norm2_tr = norm(TR_CHANNELS[2])
+        self.block2_tr = block(TR_CHANNELS[2])
+        self.conv1_tr = conv(CHANNELS[1] + TR_CHANNELS[2], TR_CHANNELS[1], 1)
+        self.final = conv(TR_CHANNELS[1], out_channels, 1, bias=True)
+
+    def forward(self, x):
+        """model/resunet.py:142-193.  The MEF.relu calls after each block (:146,151,156,161,166,173,180) are
+        idempotent (the block already ends in ReLU, residual_block.py:51) and therefore cost nothing here."""
+        if self.training:
+            raise NotImplementedError('eyoc_b200 implements the inference path only: call model.eval()')
+        with torch.no_grad():
+            out_s1 = self.block1(conv_bn_act(x, self.conv1, self.norm1))
+            out_s2 = self.block2(conv_bn_act(out_s1, self.conv2, self.norm2))
+            out_s4 = self.block3(conv_bn_act(out_s2, self.conv3, self.norm3))
+            out_s8 = self.block4(conv_bn_act(out_s4, self.conv4, self.norm4))
+
+            out_s4_tr = self.block4_tr(conv_bn_act(out_s8, self.conv4_tr, self.norm4_tr))
+            out_s2_tr = self.block3_tr(conv_bn_act(out_s4_tr, self.conv3_tr, self.norm3_tr, skip=out_s4))
+            out_s1_tr = self.block2_tr(conv_bn_act(out_s2_tr, self.conv2_tr, self.norm2_tr, skip=out_s2))
+
+            out = conv_bn_act(out_s1_tr, self.conv1_tr, relu=True, skip=out_s1)
+            # final 1x1 conv + bias; L2 normalisation (no epsilon, :189) fused into its epilogue
+            return conv_bn_act(out, self.final, l2norm=bool(self.normalize_feature))
+
+
+class ResUNetBN2(ResUNet2):
+    NORM_TYPE = 'BN'
+
+
+class ResUNetBN2B(ResUNet2):
+    NORM_TYPE = 'BN'
+    CHANNELS = [None, 32, 64, 128, 256]
+    TR_CHANNELS = [None, 64, 64, 64, 64]
+
+
+class ResUNetBN2C(ResUNet2):
+    NORM_TYPE = 'BN'
+    CHANNELS = [None, 32, 64, 128, 256]
+    TR_CHANNELS = [None, 64, 64, 64, 128]
+
+
+class ResUNetBN2D(ResUNet2):
+    NORM_TYPE = 'BN'
+    CHANNELS = [None, 32, 64, 128, 256]
+    TR_CHANNELS = [None, 64, 64, 128, 128]
+
+
+class ResUNetBN2E(ResUNet2):
+    NORM_TYPE = 'BN'
+    CHANNELS = [None, 128, 128, 128, 256]
+    TR_CHANNELS = [None, 64, 128, 128, 128]
+
+
+class ResUNetFatBN(ResUNet2):
+    """model/resunet.py:224-227 (used by scripts/test_waymo.sh:13)."""
+    NORM_TYPE = 'BN'
+    CHANNELS = [None, 32, 64, 128, 256]
+    TR_CHANNELS = [None, 128, 128, 128, 256]

@@ -1,0 +1,151 @@
+"""Sparse-convolution modules with MinkowskiEngine's parameter layout, executed by csrc/sparse_conv.cu.
+
+Parameter names and shapes are MinkowskiEngine's so that reference checkpoints load unchanged
+(SURVEY.md §5): ``<conv>.kernel`` [K, C_in, C_out] (2-D [C_in, C_out] when K == 1), ``<conv>.bias`` [1, C_out],
+``<norm>.bn.{weight,bias,running_mean,running_var,num_batches_tracked}``.
+Only inference (eval-mode BatchNorm) is implemented: the hot path is registration inference.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _C
+from .sparse import CoordinateMapKey, SparseTensor
+
+
+class MinkowskiConvolution(nn.Module):
+    """ME.MinkowskiConvolution(in, out, kernel_size, stride, dilation, bias, dimension) - model/resunet.py:31-37."""
+    TRANSPOSED = False
+
+    def __init__(self, in_channels, out_channels, kernel_size=-1, stride=1, dilation=1, bias=False, dimension=3):
+        super().__init__()
+        if dimension != 3 or dilation != 1:
+            raise NotImplementedError('3-D, dilation-1 convolutions only (all the reference uses)')
+        if stride not in (1, 2) or kernel_size not in (1, 3, 5, 7):
+            raise NotImplementedError(f'unsupported stride/kernel_size {stride}/{kernel_size}')
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.dimension = kernel_size, stride, dimension
+        K = kernel_size ** 3
+        shape = (in_channels, out_channels) if K == 1 else (K, in_channels, out_channels)
+        self.kernel = nn.Parameter(torch.empty(shape, dtype=torch.float32))
+        self.bias = nn.Parameter(torch.zeros((1, out_channels), dtype=torch.float32)) if bias else None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        with torch.no_grad():
+            n = self.in_channels * self.kernel_size ** 3
+            stdv = 1.0 / math.sqrt(n)
+            self.kernel.uniform_(-stdv, stdv)
+            if self.bias is not None:
+                self.bias.uniform_(-stdv, stdv)
+
+    def out_stride(self, ts_in):
+        if self.TRANSPOSED:
+            if ts_in % self.stride:
+                raise RuntimeError('transposed convolution below tensor stride 1')
+            return ts_in // self.stride
+        return ts_in * self.stride
+
+    def forward(self, x):
+        return conv_bn_act(x, self)
+
+    def extra_repr(self):
+        return f'in={self.in_channels}, out={self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}'
+
+
+class MinkowskiConvolutionTranspose(MinkowskiConvolution):
+    """ME.MinkowskiConvolutionTranspose - model/resunet.py:83-116.  Output coordinates = the cached finer map."""
+    TRANSPOSED = True
+
+
+class MinkowskiBatchNorm(nn.Module):
+    """ME.MinkowskiBatchNorm: nn.BatchNorm1d on .F (state-dict prefix ``bn.``) - model/common.py:6."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True):
+        super().__init__()
+        self.bn = nn.BatchNorm1d(num_features, eps=eps, momentum=momentum, affine=affine,
+                                 track_running_stats=track_running_stats)
+
+    def folded(self):
+        """Eval-mode BatchNorm as a per-channel affine: y = x * scale + shift."""
+        if self.training:
+            raise NotImplementedError('eyoc_b200 implements the inference path only: call model.eval()')
+        bn = self.bn
+        ver = tuple(int(t._version) for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var)) + (bn.weight.device,)
+        cache = getattr(self, '_folded', None)
+        if cache is None or cache[0] != ver:
+            with torch.no_grad():
+                scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float().contiguous()
+                shift = (bn.bias - bn.running_mean * scale).float().contiguous()
+            self._folded = (ver, scale, shift)
+            cache = self._folded
+        return cache[1], cache[2]
+
+    def forward(self, x):
+        """Stand-alone eval BatchNorm (module-level compatibility only: the fused forward folds it into the
+        producing convolution's epilogue and never calls this)."""
+        scale, shift = self.folded()
+        return SparseTensor(x.F * scale + shift, coordinate_map_key=x.coordinate_map_key,
+                            coordinate_manager=x.coordinate_manager)
+
+
+def sparse_conv_raw(in0, in1, nbr, weight, scale, shift, residual, relu, l2norm, out, row_perm=None):
+    """Thin call into eyoc_sparse_conv (include/eyoc_b200.h)."""
+    _C.require_cuda(in0, in1, nbr, weight, scale, shift, residual, out, row_perm)
+    c0 = in0.shape[1]
+    c1 = in1.shape[1] if in1 is not None else 0
+    K = 1 if weight.dim() == 2 else weight.shape[0]
+    cout = weight.shape[-1]
+    if weight.shape[-2] != c0 + c1:
+        raise RuntimeError(f'kernel expects {weight.shape[-2]} input channels, got {c0}+{c1}')
+    n_out = out.shape[0]
+    with torch.cuda.device(in0.device):
+        _C.check(_C.lib().eyoc_sparse_conv(_C.ptr(in0), _C.c_int(c0), _C.ptr(in1), _C.c_int(c1), _C.ptr(nbr), _C.c_int(K),
+                                           _C.c_int64(n_out), _C.ptr(row_perm), _C.ptr(weight), _C.ptr(scale),
+                                           _C.ptr(shift), _C.ptr(residual), _C.c_int(int(relu)), _C.c_int(int(l2norm)),
+                                           _C.ptr(out), _C.c_int(cout), _C.stream()))
+    return out
+
+
+def conv_bn_act(x, conv, norm=None, residual=None, relu=False, l2norm=False, skip=None):
+    """One fused launch: conv (+ fused concat with ``skip``) -> BN affine / bias -> + residual -> ReLU -> L2 norm.
+
+    x, skip, residual are SparseTensors; returns a SparseTensor on the output coordinate map."""
+    mgr = x.coordinate_manager
+    ts_in = x.coordinate_map_key.tensor_stride
+    ts_out = conv.out_stride(ts_in)
+    nbr = None
+    row_perm = None
+    if conv.kernel_size > 1 or ts_out != ts_in:
+        nbr = mgr.kernel_map(ts_in, ts_out, conv.kernel_size, transposed=conv.TRANSPOSED)
+        if conv.TRANSPOSED:
+            row_perm = mgr.parity_perm(ts_out)
+    mgr.ensure_levels(max(ts_in, ts_out))
+    n_out = mgr.num_rows(ts_out)
+    scale = shift = None
+    if norm is not None:
+        scale, shift = norm.folded()
+        if conv.bias is not None:
+            shift = shift + conv.bias.view(-1) * scale
+    elif conv.bias is not None:
+        shift = conv.bias.view(-1)
+    in0 = x.F if x.F.is_contiguous() else x.F.contiguous()
+    in1 = None
+    if skip is not None:
+        in1 = skip.F if skip.F.is_contiguous() else skip.F.contiguous()
+    out = torch.empty((n_out, conv.out_channels), dtype=torch.float32, device=in0.device)
+    sparse_conv_raw(in0, in1, nbr, conv.kernel.detach(), scale, shift, residual.F if residual is not None else None, relu,
+                    l2norm, out, row_perm)
+    return SparseTensor(out, coordinate_map_key=CoordinateMapKey(ts_out), coordinate_manager=mgr)
+
+
+def cat(*tensors):
+    """ME.cat (model/resunet.py:168): concatenate features of tensors on the same coordinate map.  The fused
+    forward never materialises this (conv_bn_act(skip=...)); provided for module-level use."""
+    key = tensors[0].coordinate_map_key
+    for t in tensors:
+        if t.coordinate_map_key != key or t.coordinate_manager is not tensors[0].coordinate_manager:
+            raise RuntimeError('ME.cat: tensors live on different coordinate maps')
+    return SparseTensor(torch.cat([t.F for t in tensors], 1), coordinate_map_key=key,
+                        coordinate_manager=tensors[0].coordinate_manager)

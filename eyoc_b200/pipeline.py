@@ -1,0 +1,141 @@
+"""Batched registration pipeline: the per-pair loop of the reference's scripts/test_kitti.py:130-181 executed for
+a whole block of independent pairs at once, and sharded over GPUs by pair.
+
+Per pair the reference does: 2 x ResUNetBN2C forward -> find_corr (5000-subsample NN, diagnostic) ->
+random_sample(5000) x2 -> Matcher.estimator (8000 with-replacement resample, NN matching, SC2-PCR, labels).
+Here the 2P clouds of P pairs go through ONE batched forward (batch column in the coordinates), the six host
+RNG draws of every pair are made up front in the reference's order (so a sequential reference loop seeded the
+same way sees the same indices), the index compositions are applied by a single gather, and the matching and
+SC2-PCR kernels run batched over P.
+"""
+import numpy as np
+import torch
+
+from . import _C
+from .lib.eval import knn1
+from .sparse import SparseTensor
+
+RECORD_FLOATS = 24     # T (16) | n_inliers | best_seed | pair_id | status | nn_hit_ratio | 3 pad
+
+
+def shard_range(num_pairs, world_size, rank):
+    """Contiguous block of pair ids owned by ``rank``; blocks differ by at most one pair."""
+    base, rem = divmod(num_pairs, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def draw_indices(n0, n1, subsample_size, num_sample, num_node):
+    """The host RNG draws of one pair, in the reference's order:
+    find_corr (test_kitti.py:33-34), random_sample x2 (:159-160 -> :69-71), match_pair (SC2_PCR.py:288-289)."""
+    d = {}
+    if subsample_size > 0 and n0 > subsample_size:
+        d['fc0'] = np.random.choice(n0, min(n0, subsample_size), replace=False)
+        d['fc1'] = np.random.choice(n1, min(n1, subsample_size), replace=False)
+    else:
+        d['fc0'], d['fc1'] = np.arange(n0), np.arange(n1)
+    for key, n in (('rs0', n0), ('rs1', n1)):
+        if n == num_sample:
+            d[key] = np.arange(n)
+        else:
+            d[key] = np.random.permutation(n)[:num_sample] if n > num_sample else np.random.choice(n, num_sample)
+    if num_node == 'all':
+        d['mp0'], d['mp1'] = np.arange(num_sample), np.arange(num_sample)
+    else:
+        d['mp0'] = np.random.choice(num_sample, num_node)
+        d['mp1'] = np.random.choice(num_sample, num_node)
+    return d
+
+
+class RegistrationPipeline:
+    """features -> matching -> SC2-PCR for blocks of pairs on one GPU."""
+
+    def __init__(self, model, matcher, subsample_size=5000, num_sample=5000, run_find_corr=True):
+        self.model, self.matcher = model, matcher
+        self.subsample_size, self.num_sample, self.run_find_corr = subsample_size, num_sample, run_find_corr
+
+    def plan(self, sizes):
+        """Host side of one block: RNG draws + index composition.  sizes = [(n0, n1), ...] -> dict of int64 arrays
+        holding GLOBAL row indices into the concatenated [cloud0_0, cloud1_0, cloud0_1, cloud1_1, ...] features."""
+        P = len(sizes)
+        nn_ = self.matcher.num_node
+        offs = np.zeros(2 * P + 1, np.int64)
+        offs[1:] = np.cumsum([n for pair in sizes for n in pair])
+        fc0, fc1, src, tgt = [], [], [], []
+        for p, (n0, n1) in enumerate(sizes):
+            d = draw_indices(n0, n1, self.subsample_size, self.num_sample, nn_)
+            fc0.append(d['fc0'] + offs[2 * p])
+            fc1.append(d['fc1'] + offs[2 * p + 1])
+            src.append(d['rs0'][d['mp0']] + offs[2 * p])
+            tgt.append(d['rs1'][d['mp1']] + offs[2 * p + 1])
+        same = len({len(a) for a in fc0}) == 1 and len({len(a) for a in fc1}) == 1
+        return dict(offsets=offs, fc0=fc0, fc1=fc1, src=np.stack(src), tgt=np.stack(tgt), fc_uniform=same)
+
+    def run(self, coords, xyz, sizes, plan=None, descriptors=None):
+        """coords [sum N, 4] int32 (batch column = cloud id 0..2P-1), xyz [sum N, 3] fp32, both CUDA, clouds
+        ordered [c0 of pair 0, c1 of pair 0, c0 of pair 1, ...].  Returns a dict of CUDA tensors.
+        ``descriptors`` (optional [sum N, 32]) replaces the network output downstream of the forward pass (used
+        by the benchmark to give the estimator a realistic inlier ratio with random-init weights); the forward
+        pass is executed regardless."""
+        plan = plan or self.plan(sizes)
+        dev = coords.device
+        P = len(sizes)
+        feats_in = torch.ones((coords.shape[0], 1), dtype=torch.float32, device=dev)
+        F = self.model(SparseTensor(feats_in, coordinates=coords)).F
+        Fm = F if descriptors is None else descriptors
+        out = {'features': F}
+        if self.run_find_corr:                                   # diagnostic NN of the reference (test_kitti.py:153-154)
+            if plan['fc_uniform']:
+                i0 = torch.from_numpy(np.stack(plan['fc0'])).to(dev)
+                i1 = torch.from_numpy(np.stack(plan['fc1'])).to(dev)
+                nn_idx = knn1(Fm[i0], Fm[i1], form=0)
+                out['find_corr_src'] = i0
+                out['find_corr_tgt'] = torch.gather(i1, 1, nn_idx)
+            else:
+                s_, t_ = [], []
+                for a, b in zip(plan['fc0'], plan['fc1']):
+                    a, b = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+                    s_.append(a)
+                    t_.append(b[knn1(Fm[a], Fm[b], form=0)])
+                out['find_corr_src'], out['find_corr_tgt'] = s_, t_
+        src_idx = torch.from_numpy(plan['src']).to(dev)          # [P, num_node]
+        tgt_idx = torch.from_numpy(plan['tgt']).to(dev)
+        nn_idx = knn1(Fm[src_idx], Fm[tgt_idx], form=1)          # SC2_PCR.py:296-298
+        corr_tgt = torch.gather(tgt_idx, 1, nn_idx)
+        src_corr, tgt_corr = xyz[src_idx], xyz[corr_tgt]
+        trans, fitness, labels = self.matcher._run(src_corr, tgt_corr, want_labels=True)
+        out.update(trans=trans, labels=labels, fitness=fitness, src_corr_idx=src_idx, tgt_corr_idx=corr_tgt,
+                   src_corr=src_corr, tgt_corr=tgt_corr)
+        return out
+
+    @staticmethod
+    def records(out, pair_ids):
+        """Fixed-size per-pair result records [P, RECORD_FLOATS] fp32 (what the single NCCL all-gather carries)."""
+        P = out['trans'].shape[0]
+        rec = torch.zeros((P, RECORD_FLOATS), dtype=torch.float32, device=out['trans'].device)
+        rec[:, :16] = out['trans'].reshape(P, 16)
+        rec[:, 16] = out['labels'].sum(1)
+        rec[:, 17] = out['fitness'].argmax(1).float()
+        rec[:, 18] = torch.as_tensor(pair_ids, dtype=torch.float32, device=rec.device)
+        rec[:, 19] = 1.0
+        return rec
+
+
+def gather_records(rec, num_pairs, group=None):
+    """The path's only collective: ONE all-gather of the per-pair records.  Every rank pads its block to
+    ceil(num_pairs / world) rows (block sizes follow from ``shard_range``, so no size exchange is needed);
+    the padding is stripped after the gather.  NCCL on GPUs, gloo in the CPU tests."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return rec
+    world = dist.get_world_size(group)
+    m = -(-num_pairs // world)
+    pad = torch.zeros((m, rec.shape[1]), dtype=rec.dtype, device=rec.device)
+    pad[:rec.shape[0]] = rec
+    buf = torch.empty((world * m, rec.shape[1]), dtype=rec.dtype, device=rec.device)
+    dist.all_gather_into_tensor(buf, pad, group=group)
+    keep = []
+    for r in range(world):
+        lo, hi = shard_range(num_pairs, world, r)
+        keep.append(buf[r * m: r * m + (hi - lo)])
+    return torch.cat(keep, 0)

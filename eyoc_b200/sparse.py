@@ -1,0 +1,253 @@
+"""Sparse-tensor plumbing with the MinkowskiEngine surface the reference touches.
+
+``SparseTensor(features, coordinates=...)`` (scripts/test_kitti.py:143-147), ``.F`` / ``.C`` /
+``coordinate_map_key`` / ``coordinate_manager`` / ``decomposed_coordinates_and_features``
+(model/resunet.py:188-191, lib/trainer.py:1289), plus the coordinate manager that owns the per-level
+coordinate hashes and the cached kernel maps (8 maps per batch, each reused by 1-5
+convolutions).  All device work goes through the C-ABI (csrc/coordmap.cu); there is no CPU path.
+"""
+import numpy as np
+import torch
+
+from . import _C
+
+
+def _pow2_at_least(x):
+    c = 2
+    while c < x:
+        c *= 2
+    return c
+
+
+class CoordinateMapKey:
+    """(tensor_stride,) identifier of one coordinate set inside a manager."""
+
+    def __init__(self, tensor_stride):
+        self.tensor_stride = int(tensor_stride)
+
+    def get_tensor_stride(self):
+        return [self.tensor_stride] * 3
+
+    def __eq__(self, other):
+        return isinstance(other, CoordinateMapKey) and other.tensor_stride == self.tensor_stride
+
+    def __hash__(self):
+        return hash(self.tensor_stride)
+
+    def __repr__(self):
+        return f'CoordinateMapKey(tensor_stride={self.tensor_stride})'
+
+
+class _Level:
+    __slots__ = ('coords', 'n', 'keys', 'vals', 'cap', 'ts')
+
+
+class CoordinateManager:
+    """Per-batch coordinate sets (tensor stride 1, 2, 4, ...) and kernel maps, all resident on one GPU."""
+
+    def __init__(self, coordinates):
+        if not coordinates.is_cuda:
+            raise RuntimeError('eyoc_b200.SparseTensor needs CUDA coordinates (no CPU fallback)')
+        if coordinates.dim() != 2 or coordinates.shape[1] != 4:
+            raise RuntimeError('coordinates must be [N, 4] (batch, x, y, z)')
+        self.device = coordinates.device
+        self.levels = {}
+        self._maps = {}
+        self._perms = {}
+        self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        c = coordinates.to(torch.int32).contiguous()
+        lv = _Level()
+        lv.coords, lv.n, lv.ts = c, c.shape[0], 1
+        lv.cap = _pow2_at_least(2 * max(lv.n, 1))
+        lv.keys = torch.empty(lv.cap, dtype=torch.int64, device=self.device)
+        lv.vals = torch.empty(lv.cap, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _C.check(_C.lib().eyoc_hash_build(_C.ptr(c), _C.c_int64(lv.n), _C.ptr(lv.keys), _C.ptr(lv.vals),
+                                              _C.c_int64(lv.cap), _C.ptr(self._status), _C.stream()))
+        self.levels[1] = lv
+        self._checked = False
+
+    # ------------------------------------------------------------------ levels
+    def _check_status(self):
+        if not self._checked:
+            st = int(self._status.item())
+            if st & 1:
+                raise RuntimeError('coordinates outside the packed 16-bit range (batch 0..65535, xyz -32768..32767)')
+            if st & 2:
+                raise RuntimeError('duplicate coordinates: quantise first (sparse_quantize)')
+            self._checked = True
+
+    def ensure_levels(self, max_stride):
+        """Build the stride-2 coordinate sets up to ``max_stride`` (one 4-byte D2H read per new level: the row
+        count sizes the next level's buffers, as in MinkowskiEngine's host-side coordinate manager)."""
+        ts = 1
+        lib = _C.lib()
+        with torch.cuda.device(self.device):
+            while ts < max_stride:
+                fine = self.levels[ts]
+                ts2 = ts * 2
+                if ts2 not in self.levels:
+                    lv = _Level()
+                    lv.ts = ts2
+                    lv.cap = _pow2_at_least(2 * max(fine.n, 1))
+                    lv.keys = torch.empty(lv.cap, dtype=torch.int64, device=self.device)
+                    lv.vals = torch.empty(lv.cap, dtype=torch.int32, device=self.device)
+                    coords = torch.empty((fine.n, 4), dtype=torch.int32, device=self.device)
+                    n_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+                    ws = torch.empty(max(lib.eyoc_downsample_workspace_bytes(_C.c_int64(fine.n)), 8), dtype=torch.uint8,
+                                     device=self.device)
+                    _C.check(lib.eyoc_coords_downsample(_C.ptr(fine.coords), _C.c_int64(fine.n), _C.c_int(ts2),
+                                                        _C.ptr(lv.keys), _C.ptr(lv.vals), _C.c_int64(lv.cap),
+                                                        _C.ptr(coords), _C.ptr(n_dev), _C.ptr(ws),
+                                                        _C.c_size_t(ws.numel()), _C.stream()))
+                    lv.n = int(n_dev.item())
+                    lv.coords = coords[:lv.n]
+                    self.levels[ts2] = lv
+                ts = ts2
+        self._check_status()
+
+    def num_rows(self, ts):
+        return self.levels[ts].n
+
+    # ------------------------------------------------------------------ kernel maps
+    def kernel_map(self, ts_in, ts_out, ksize, transposed=False):
+        """nbr [K, N_out] int32.  Forward: rows of the ts_in map at c_out + off*ts_in.  Transposed (ts_out < ts_in):
+        rows of the coarse ts_in map at c_out - off*ts_out, same k (MinkowskiEngine convention, no flip)."""
+        key = (ts_in, ts_out, ksize, transposed)
+        if key not in self._maps:
+            self.ensure_levels(max(ts_in, ts_out))
+            lin, lout = self.levels[ts_in], self.levels[ts_out]
+            step = -ts_out if transposed else ts_in
+            K = ksize ** 3
+            nbr = torch.empty((K, lout.n), dtype=torch.int32, device=self.device)
+            with torch.cuda.device(self.device):
+                _C.check(_C.lib().eyoc_kernel_map(_C.ptr(lout.coords), _C.c_int64(lout.n), _C.ptr(lin.keys), _C.ptr(lin.vals),
+                                                  _C.c_int64(lin.cap), _C.c_int(ksize), _C.c_int(step), _C.ptr(nbr),
+                                                  _C.stream()))
+            self._maps[key] = nbr
+        return self._maps[key]
+
+    def parity_perm(self, ts):
+        """Row order of level ``ts`` grouped by parity class (CTA-uniform offsets for transposed convs)."""
+        if ts not in self._perms:
+            lv = self.levels[ts]
+            cls = torch.empty(lv.n, dtype=torch.int32, device=self.device)
+            with torch.cuda.device(self.device):
+                _C.check(_C.lib().eyoc_parity_class(_C.ptr(lv.coords), _C.c_int64(lv.n), _C.c_int(ts), _C.ptr(cls),
+                                                    _C.stream()))
+            self._perms[ts] = torch.sort(cls, stable=True)[1].to(torch.int32)
+        return self._perms[ts]
+
+
+class SparseTensor:
+    """Features [N, C] fp32 on a coordinate set; row order == input order (the reference relies on it)."""
+
+    def __init__(self, features, coordinates=None, coordinate_map_key=None, coordinate_manager=None, device=None,
+                 tensor_stride=1):
+        if device is not None:
+            features = features.to(device)
+            coordinates = coordinates.to(device) if coordinates is not None else None
+        _C.require_cuda(features)
+        if coordinate_manager is None:
+            if coordinates is None:
+                raise RuntimeError('SparseTensor needs coordinates or a coordinate_manager')
+            coordinate_manager = CoordinateManager(coordinates.to(features.device))
+            coordinate_map_key = CoordinateMapKey(tensor_stride)
+        elif coordinate_map_key is None:
+            coordinate_map_key = CoordinateMapKey(tensor_stride)
+        self._F = features
+        self.coordinate_manager = coordinate_manager
+        self.coordinate_map_key = coordinate_map_key
+        n = coordinate_manager.levels[coordinate_map_key.tensor_stride].coords.shape[0]
+        if features.shape[0] != n:
+            raise RuntimeError(f'features have {features.shape[0]} rows, coordinates {n}')
+
+    @property
+    def F(self):
+        return self._F
+
+    @property
+    def C(self):
+        return self.coordinate_manager.levels[self.coordinate_map_key.tensor_stride].coords
+
+    @property
+    def coordinates(self):
+        return self.C
+
+    @property
+    def features(self):
+        return self._F
+
+    @property
+    def device(self):
+        return self._F.device
+
+    @property
+    def tensor_stride(self):
+        return self.coordinate_map_key.get_tensor_stride()
+
+    def __len__(self):
+        return self._F.shape[0]
+
+    @property
+    def shape(self):
+        return self._F.shape
+
+    @property
+    def decomposed_coordinates_and_features(self):
+        """Per-batch-index lists (lib/trainer.py:1289)."""
+        C, F = self.C, self._F
+        nb = int(C[:, 0].max().item()) + 1 if len(C) else 0
+        coords, feats = [], []
+        for b in range(nb):
+            m = C[:, 0] == b
+            coords.append(C[m, 1:])
+            feats.append(F[m])
+        return coords, feats
+
+    @property
+    def decomposed_features(self):
+        return self.decomposed_coordinates_and_features[1]
+
+    @property
+    def decomposed_coordinates(self):
+        return self.decomposed_coordinates_and_features[0]
+
+
+# ---------------------------------------------------------------------------------- ME.utils (host-side prep)
+def sparse_quantize(coordinates, features=None, return_index=False, quantization_size=None):
+    """ME.utils.sparse_quantize as the reference uses it (lib/data_loaders.py:940): floor, unique rows, FIRST
+    occurrence kept, index returned in ascending order."""
+    is_torch = isinstance(coordinates, torch.Tensor)
+    c = coordinates.cpu().numpy() if is_torch else np.asarray(coordinates)
+    if quantization_size is not None:
+        c = c / quantization_size
+    q = np.floor(c).astype(np.int32)
+    _, first = np.unique(q, axis=0, return_index=True)
+    sel = np.sort(first)
+    out = torch.from_numpy(q[sel]) if is_torch else q[sel]
+    if return_index:
+        idx = torch.from_numpy(sel) if is_torch else sel
+        return (out, idx) if features is None else (out, features[sel], idx)
+    return out if features is None else (out, features[sel])
+
+
+def batched_coordinates(coords, dtype=torch.int32, device=None):
+    """ME.utils.batched_coordinates: prepend the batch index -> int32 [sum N, 4]."""
+    out = []
+    for b, c in enumerate(coords):
+        c = torch.as_tensor(c).to(dtype)
+        out.append(torch.cat([torch.full((len(c), 1), b, dtype=dtype), c], 1))
+    out = torch.cat(out, 0) if out else torch.zeros((0, 4), dtype=dtype)
+    return out.to(device) if device is not None else out
+
+
+def sparse_collate(coords, feats, labels=None, dtype=torch.int32, device=None):
+    """ME.utils.sparse_collate (lib/data_loaders.py:65-66): batched coordinates + concatenated features."""
+    C = batched_coordinates(coords, dtype=dtype, device=device)
+    F = torch.cat([torch.as_tensor(f) for f in feats], 0)
+    if device is not None:
+        F = F.to(device)
+    if labels is not None:
+        return C, F, torch.cat([torch.as_tensor(l) for l in labels], 0)
+    return C, F

@@ -87,6 +87,39 @@ int eyoc_sc2pcr(const float* src, const float* tgt, int batch, int n, int num_se
 int eyoc_kabsch_batched(const float* A, const float* B, float* w, int batch, int n, float weight_threshold,
                         float* T, eyoc_stream_t stream);
 
+/* ---------------------------------------------------------------- coordinate maps / kernel maps
+ * Replace MinkowskiEngine's coordinate manager under ME.SparseTensor(F, coordinates=C)
+ * (scripts/test_kitti.py:143-147) and under every ME.MinkowskiConvolution[Transpose] of
+ * model/resunet.py:31-140.  coords are [n, 4] int32 (batch, x, y, z), 16-bit range per field.
+ * Hash table: open addressing, capacity a power of two >= 2n; keys[capacity] u64, vals[capacity] i32.
+ * status (device int32, caller-zeroed): bit 0 = coordinate out of range, bit 1 = duplicate coordinate. */
+int eyoc_hash_build(const int32_t* coords, int64_t n, uint64_t* table_keys, int32_t* table_vals, int64_t capacity,
+                    int32_t* status, eyoc_stream_t stream);
+/* Stride-2 coordinate set unique(floor(c / ts_out) * ts_out) in first-occurrence order (+ its hash table).
+ * coords_out has room for n rows; *n_out (device) receives the row count. */
+size_t eyoc_downsample_workspace_bytes(int64_t n);
+int eyoc_coords_downsample(const int32_t* coords, int64_t n, int ts_out, uint64_t* table_keys, int32_t* table_vals,
+                           int64_t capacity, int32_t* coords_out, int32_t* n_out, void* workspace, size_t workspace_bytes,
+                           eyoc_stream_t stream);
+/* nbr[k, o] = row in the input map of (c_o + off_k * step), else -1;  k = ix + K*(iy + K*iz), off = (ix,iy,iz) - (K-1)/2.
+ * step = +tensor_stride_in for a forward convolution, -tensor_stride_out for a transposed one. */
+int eyoc_kernel_map(const int32_t* out_coords, int64_t n_out, const uint64_t* in_table_keys, const int32_t* in_table_vals,
+                    int64_t capacity, int ksize, int step, int32_t* nbr, eyoc_stream_t stream);
+/* cls[i] = parity class (3 bits) of coords[i] / ts: groups the rows of a transposed stride-2 convolution by
+ * their set of admissible kernel offsets. */
+int eyoc_parity_class(const int32_t* coords, int64_t n, int ts, int32_t* cls, eyoc_stream_t stream);
+
+/* ---------------------------------------------------------------- sparse convolution + fused epilogue
+ * Replaces ME.MinkowskiConvolution / MinkowskiConvolutionTranspose forward (model/resunet.py:31-140) fused with
+ * what follows it in model/resunet.py:142-193 and model/residual_block.py:37-53:
+ *   out[o] = l2norm?( relu?( (sum_k [in0 | in1][nbr[k, o]] @ W[k]) * scale + shift + residual[o] ) )
+ * in0 [n_in, c0], in1 [n_in, c1] or NULL (fused ME.cat), weight [K, c0 + c1, cout], scale/shift [cout] or NULL
+ * (folded eval BatchNorm; shift alone = bias), residual [n_out, cout] or NULL, nbr NULL = identity (K == 1),
+ * row_perm [n_out] or NULL = order in which output rows are tiled (results do not depend on it). */
+int eyoc_sparse_conv(const float* in0, int c0, const float* in1, int c1, const int32_t* nbr, int K, int64_t n_out,
+                     const int32_t* row_perm, const float* weight, const float* scale, const float* shift,
+                     const float* residual, int relu, int l2norm, float* out, int cout, eyoc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
