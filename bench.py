@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py — pairs/sec of the EYOC registration-inference hot path on synthetic KITTI-shaped pairs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs-per-gpu 64] [--impl ours|reference]
+
+One step = one pass of the whole hot path (2 x ResUNetBN2C forward per pair -> find_corr NN -> resample ->
+match_pair NN -> SC2-PCR -> inlier labels) over a block of `pairs-per-gpu` synthetic pairs (~30 k voxels per cloud,
+0.3 m voxels).  Weak scaling: every rank owns its own block (BASELINE.json configs[2] at N=1, configs[3] at N=8);
+the only collective is one all-gather of per-pair result records.
+
+`value`  : pairs/s with inputs (coordinates, points, index plans) already resident in HBM, CUDA-event timed.
+`e2e`    : pairs/s through the public Python API with HOST inputs: H2D of coordinates/points from pinned memory,
+           host RNG index planning, and the D2H read of the result records are inside the timed region.
+`roofline`: the sparse-convolution gather-GEMM kernels, CUDA-event timed inside the timed region.
+`cpu_baseline` / `--impl reference`: the oracle port of the reference path (torch-CPU) on this box's host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+KITTI_CFG = dict(inlier_threshold=0.6, num_node=8000, use_mutual=False, d_thre=0.1, num_iterations=20, ratio=0.2,
+                 nms_radius=0.6, max_points=8000, k1=30, k2=20)      # scripts/SC2_PCR/config_json/config_KITTI.json
+WORKLOAD = 'batch of synthetic KITTI pairs (~30k voxels/cloud, 0.3 m): ResUNetBN2C 32-D + find_corr NN + match_pair NN + SC2-PCR'
+
+
+def _peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons during the timed region (pynvml; falls back to nvidia-smi)."""
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap',
+               0x80: 'hw_power_brake_slowdown'}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                if self.nv is not None:
+                    self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                    try:
+                        r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, name in self.REASONS.items():
+                        if r & bit:
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(s)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_pair(pair, sd):
+    """The reference path for ONE pair on the CPU through the oracle port (oracle/*.py restates
+    model/resunet.py + MinkowskiEngine semantics, lib/eval.py, scripts/test_kitti.py, scripts/SC2_PCR/SC2_PCR.py)."""
+    import numpy as np
+    import torch
+    from eyoc_b200 import synth
+    from oracle import matching_oracle as MO, resunet_oracle as RO, sc2pcr_oracle as O
+    feats = []
+    for c in (pair['coords0'], pair['coords1']):
+        cb = synth.collate([c])
+        feats.append(RO.resunet_forward(cb, torch.ones(len(cb), 1), sd, True, 5))
+    F0, F1 = (torch.from_numpy(pair['desc0']), torch.from_numpy(pair['desc1'])) if 'desc0' in pair else feats
+    xyz0, xyz1 = pair['xyz0'], pair['xyz1']
+    MO.find_corr(xyz0, xyz1, F0, F1, subsample_size=5000)
+    x0, f0 = MO.random_sample(xyz0, F0, 5000)
+    x1, f1 = MO.random_sample(xyz1, F1, 5000)
+    cfg = O.SC2Config(**{k: KITTI_CFG[k] for k in ('inlier_threshold', 'num_node', 'd_thre', 'num_iterations', 'ratio',
+                                                   'nms_radius', 'max_points', 'k1', 'k2')})
+    T, labels, _, _, _ = O.estimator(torch.from_numpy(x0)[None], torch.from_numpy(x1)[None], f0[None], f1[None], cfg,
+                                     dense_weight=False)
+    return T[0], labels[0]
+
+
+def cpu_state_dict(seed=0):
+    from oracle import resunet_oracle as RO
+    return RO.make_state_dict(1, 32, 5, seed=seed)
+
+
+def run_cpu(pair_ids, warmup=0):
+    import numpy as np
+    import torch
+    from eyoc_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pairs = synth.make_pairs(pair_ids)
+    sd = cpu_state_dict()
+    np.random.seed(0)
+    for p in pairs[:warmup]:
+        cpu_pair(p, sd)
+    t0 = time.perf_counter()
+    for p in pairs[warmup:]:
+        cpu_pair(p, sd)
+    dt = time.perf_counter() - t0
+    n = len(pairs) - warmup
+    return n / dt, dt, n, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    ids = list(range(W + K))
+    pps, dt, n, cores = run_cpu(ids, warmup=W)
+    sample = f'{n} timed pairs (1 pair per step) after {W} warm-up pairs; oracle port of the reference path, torch-CPU fp32'
+    line = {'impl': 'reference', 'metric': 'point-cloud pairs/sec', 'value': pps, 'unit': 'pairs/s', 'n_gpus': args.gpus, 'steps': K,
+            'warmup': W, 'ms_per_step': 1e3 * dt / max(n, 1), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': WORKLOAD, 'pairs_per_step': 1},
+            'cpu_baseline': {'value': pps, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': pps, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------- our arm
+def build_model(device, seed=0):
+    import torch
+    from eyoc_b200.model import load_model
+    torch.manual_seed(seed)
+    model = load_model('ResUNetBN2C')(1, 32, bn_momentum=0.05, normalize_feature=True, conv1_kernel_size=5, D=3)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():      # non-trivial BatchNorm statistics (random-init weights; no checkpoint is reachable)
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+                m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+    return model.to(device).eval()
+
+
+def conv_algorithmic_bytes(meta, m_cache):
+    """B = 4 (M C_in + N_out C_out + K C_in C_out) + 8 M  (+ 4 N_out C_out residual read);
+    M = measured number of (in, out) kernel-map pairs."""
+    nbr = meta['nbr']
+    if nbr is None:
+        M = meta['n_out']
+    else:
+        key = nbr.data_ptr()
+        if key not in m_cache:
+            m_cache[key] = int((nbr >= 0).sum().item())
+        M = m_cache[key]
+    b = 4 * (M * meta['cin'] + meta['n_out'] * meta['cout'] + meta['K'] * meta['cin'] * meta['cout']) + 8 * M
+    if meta['residual']:
+        b += 4 * meta['n_out'] * meta['cout']
+    return b, 2 * M * meta['cin'] * meta['cout']
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from eyoc_b200 import _C, nn as enn, synth
+    from eyoc_b200.pipeline import RegistrationPipeline, gather_records, plan_to_device
+    from eyoc_b200.scripts.SC2_PCR.SC2_PCR import Matcher
+    from eyoc_b200.scripts.test_kitti import is_success, rte_rre
+
+    rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (eyoc_b200 has no CPU path; use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _C.lib()
+    P = args.pairs_per_gpu
+    K, W = args.steps, max(args.warmup, 3)
+    pairs = synth.make_pairs(list(range(rank * P, rank * P + P)))
+    coords_np, xyz_np, desc_np, sizes = synth.collate_pairs(pairs)
+    T_gt = np.stack([p['T_gt'] for p in pairs])
+    coords_h, xyz_h = torch.from_numpy(coords_np).pin_memory(), torch.from_numpy(xyz_np).pin_memory()
+    coords_d, xyz_d = coords_h.to(dev), xyz_h.to(dev)
+    desc_d = torch.from_numpy(desc_np).to(dev) if args.descriptors == 'planted' else None
+    model = build_model(dev)
+    pipe = RegistrationPipeline(model, Matcher(**KITTI_CFG))
+    np.random.seed(1000 + rank)
+    plan_d = plan_to_device(pipe.plan(sizes), dev)
+    rec_host = torch.empty((P, 24), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        out = pipe.run(coords_d, xyz_d, sizes, plan=plan_d, descriptors=desc_d)
+        rec = pipe.records(out, list(range(rank * P, rank * P + P)))
+        return gather_records(rec, P * world), out
+
+    def step_e2e():
+        c = coords_h.to(dev, non_blocking=True)
+        x = xyz_h.to(dev, non_blocking=True)
+        out = pipe.run(c, x, sizes, plan=None, descriptors=desc_d)       # plan=None: host RNG draws + composition now
+        rec = pipe.records(out, list(range(rank * P, rank * P + P)))
+        allrec = gather_records(rec, P * world)
+        rec_host.copy_(allrec[rank * P: rank * P + P] if world > 1 else allrec, non_blocking=True)
+        torch.cuda.synchronize()
+        return rec_host
+
+    for _ in range(W):
+        step_resident()
+    # ---- device-resident timing (value) + per-kernel events for the roofline
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    enn.PROFILE = []
+    launches0 = lib.eyoc_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ev = []
+    ev0.record()
+    for _ in range(K):
+        allrec, out = step_resident()
+    ev1.record()
+    barrier()
+    launches = int(lib.eyoc_launch_count() - launches0)
+    prof, enn.PROFILE = enn.PROFILE, None
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = P * world * K / (ms / 1e3)
+
+    # ---- end-to-end timing through the public API with host inputs
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        rec_e2e = step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e = P * world * K / e2e_s
+
+    # ---- roofline of the sparse-conv gather-GEMM kernels (events recorded inside the timed region)
+    m_cache, tot_ms, tot_bytes, tot_flops, n_tiled = {}, 0.0, 0, 0, 0
+    for e0, e1, meta in prof:
+        if meta['cin'] % 32 or meta['cout'] % 32:
+            continue                                            # conv1 (1->32) runs on the generic kernel
+        b, f = conv_algorithmic_bytes(meta, m_cache)
+        tot_ms += e0.elapsed_time(e1)
+        tot_bytes += b
+        tot_flops += f
+        n_tiled += 1
+    peak, peak_src = _peaks()
+    achieved = tot_bytes / (tot_ms / 1e3) / 1e9 if tot_ms > 0 else 0.0
+    roofline = {'bound': 'hbm', 'kernel': 'sparse_conv_tiled_kernel (all tiled conv launches of the timed region)',
+                'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                'peak_source': peak_src, 'launches_timed': n_tiled, 'avg_launch_ms': tot_ms / max(n_tiled, 1),
+                'share_of_step': tot_ms / ms if ms > 0 else None,
+                'algorithmic_bytes_per_step': tot_bytes // max(K, 1), 'achieved_tflops_fp32': tot_flops / (tot_ms / 1e3) / 1e12 if tot_ms > 0 else 0.0}
+
+    # ---- accuracy on this rank's block (vs ground truth; parity vs the oracle lives in tests/)
+    Ts = out['trans'].cpu()
+    rtes, rres, succ = [], [], 0
+    for i in range(P):
+        rte, rre = rte_rre(Ts[i], torch.from_numpy(T_gt[i]))
+        rtes.append(rte)
+        rres.append(np.degrees(rre))
+        succ += is_success(rte, rre)
+    line = {'metric': 'point-cloud pairs/sec', 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic KITTI-shaped LiDAR pairs (ray-cast generator, seeded); random-init weights'
+                    + ('; estimator fed planted descriptors (the forward pass still runs and is timed)' if desc_d is not None else ''),
+            'config': {'workload': WORKLOAD, 'pairs_per_gpu': P, 'global_pairs': P * world, 'voxels_per_step_per_gpu': int(coords_np.shape[0]),
+                       'parallelism': f'pair-sharded x{world}', 'l2': 'per-step working set (>= 1 GB of level-1 features) exceeds the 126 MB L2; no explicit flush',
+                       'value_mode': 'coordinates, points and index plans resident in HBM'},
+            'e2e': {'value': e2e, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(coords_np.nbytes + xyz_np.nbytes + 2 * 8 * P * 8000 + 2 * 8 * P * 5000),
+                    'd2h_bytes_per_step': int(rec_host.numel() * 4), 'ms_per_step': 1e3 * e2e_s / K},
+            'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
+            'accuracy': {'rr_vs_gt': succ / P, 'rte_m_median': float(np.median(rtes)), 'rre_deg_median': float(np.nanmedian(rres))}}
+    if world == 1 and not args.no_cpu_baseline:
+        pps, dt, n, cores = run_cpu([0, 1, 2][:args.cpu_pairs + 1], warmup=1)
+        line['cpu_baseline'] = {'value': pps, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
+                                'sample': f'{n} pairs of the same generator after 1 warm-up pair ({dt:.1f} s); oracle port of the reference path (ME-algorithm restatement + SC2_PCR restatement), torch-CPU fp32'}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--pairs-per-gpu', type=int, default=64)
+    ap.add_argument('--descriptors', default='planted', choices=['planted', 'network'])
+    ap.add_argument('--cpu-pairs', type=int, default=2)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.gpus > 1 and 'RANK' not in os.environ:        # convenience: self-launch one rank per GPU
+        os.execvp(sys.executable, [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
+                                   '--master-addr', '127.0.0.1', '--master-port', '29517', os.path.abspath(__file__)] + sys.argv[1:])
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

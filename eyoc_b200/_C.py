@@ -50,6 +50,7 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.eyoc_last_error.restype = ctypes.c_char_p
         _lib.eyoc_version.restype = c_int
+        _lib.eyoc_launch_count.restype = ctypes.c_ulonglong
         for name in ('eyoc_knn1_workspace_bytes', 'eyoc_sc2pcr_workspace_bytes', 'eyoc_downsample_workspace_bytes'):
             if hasattr(_lib, name):
                 getattr(_lib, name).restype = c_size_t

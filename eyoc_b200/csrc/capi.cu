@@ -12,7 +12,11 @@ void eyoc_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+unsigned long long g_eyoc_launches = 0;
+
 extern "C" int eyoc_version(void) { return 100; }
+
+extern "C" unsigned long long eyoc_launch_count(void) { return g_eyoc_launches; }
 
 extern "C" const char* eyoc_last_error(void) { return g_err; }
 

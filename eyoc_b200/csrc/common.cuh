@@ -30,7 +30,13 @@ void eyoc_set_error(const char* fmt, ...);
         }                                                                                \
     } while (0)
 
-#define EYOC_LAUNCH_CHECK() EYOC_CUDA(cudaGetLastError())
+// every kernel launch of the library passes through here: error check + launch accounting
+extern unsigned long long g_eyoc_launches;
+#define EYOC_LAUNCH_CHECK()            \
+    do {                               \
+        ++g_eyoc_launches;             \
+        EYOC_CUDA(cudaGetLastError()); \
+    } while (0)
 
 static inline size_t eyoc_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 

@@ -90,8 +90,26 @@ class MinkowskiBatchNorm(nn.Module):
                             coordinate_manager=x.coordinate_manager)
 
 
+# When set to a list, every sparse_conv_raw call appends (start_event, end_event, meta) - bench.py uses it to time
+# the convolution kernels with CUDA events on the launching stream inside the timed region.
+PROFILE = None
+
+
 def sparse_conv_raw(in0, in1, nbr, weight, scale, shift, residual, relu, l2norm, out, row_perm=None):
     """Thin call into eyoc_sparse_conv (include/eyoc_b200.h)."""
+    if PROFILE is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        _sparse_conv_call(in0, in1, nbr, weight, scale, shift, residual, relu, l2norm, out, row_perm)
+        ev1.record()
+        PROFILE.append((ev0, ev1, dict(K=1 if weight.dim() == 2 else weight.shape[0], cin=weight.shape[-2],
+                                       cout=weight.shape[-1], n_out=out.shape[0], nbr=nbr,
+                                       residual=residual is not None)))
+        return out
+    return _sparse_conv_call(in0, in1, nbr, weight, scale, shift, residual, relu, l2norm, out, row_perm)
+
+
+def _sparse_conv_call(in0, in1, nbr, weight, scale, shift, residual, relu, l2norm, out, row_perm=None):
     _C.require_cuda(in0, in1, nbr, weight, scale, shift, residual, out, row_perm)
     c0 = in0.shape[1]
     c1 = in1.shape[1] if in1 is not None else 0

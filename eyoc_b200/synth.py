@@ -137,3 +137,52 @@ def make_correspondences(n, inlier_ratio, seed, noise=0.03, extent=60.0, dup_rat
     T = np.eye(4)
     T[:3, :3], T[:3, 3] = R, t
     return (src[pick].astype(np.float32), tgt[pick].astype(np.float32), T.astype(np.float32), inl[pick])
+
+
+# ---------------------------------------------------------------------------------------------- bulk generation
+CACHE_DIR = '/tmp/eyoc_b200_synth'
+
+
+def _make_one(args):
+    pair_id, sigma = args
+    import os
+    path = os.path.join(CACHE_DIR, f'pair_{pair_id}_{sigma:.3f}.npz')
+    if os.path.exists(path):
+        try:
+            with np.load(path) as z:
+                return {k: z[k] for k in z.files}
+        except Exception:
+            pass
+    p = make_pair(pair_id)
+    f0, f1, hit = planted_descriptors(p['xyz0'], p['xyz1'], p['T_gt'], np.random.default_rng(99991 + pair_id), sigma=sigma)
+    p.update(desc0=f0, desc1=f1, overlap=np.float32(hit.mean()))
+    os.makedirs(CACHE_DIR, exist_ok=True)
+    tmp = path + f'.{os.getpid()}.tmp.npz'
+    np.savez(tmp, **p)
+    os.replace(tmp, path)
+    return p
+
+
+def make_pairs(pair_ids, sigma=0.12, workers=None):
+    """Generate (or load from the /tmp cache) synthetic pairs with planted descriptors, in parallel."""
+    import multiprocessing as mp
+    import os
+    workers = workers or min(len(pair_ids), os.cpu_count() or 1)
+    args = [(int(i), float(sigma)) for i in pair_ids]
+    if workers <= 1 or len(args) <= 1:
+        return [_make_one(a) for a in args]
+    with mp.get_context('fork').Pool(workers) as pool:
+        return pool.map(_make_one, args)
+
+
+def collate_pairs(pairs):
+    """[c0 of pair 0, c1 of pair 0, c0 of pair 1, ...] -> coords int32 [sum N, 4], xyz f32 [sum N, 3],
+    descriptors f32 [sum N, 32] (or None), sizes [(n0, n1), ...]."""
+    clouds = [c for p in pairs for c in (p['coords0'], p['coords1'])]
+    coords = collate(clouds)
+    xyz = np.ascontiguousarray(np.concatenate([x for p in pairs for x in (p['xyz0'], p['xyz1'])], 0), np.float32)
+    desc = None
+    if 'desc0' in pairs[0]:
+        desc = np.ascontiguousarray(np.concatenate([x for p in pairs for x in (p['desc0'], p['desc1'])], 0), np.float32)
+    sizes = [(len(p['coords0']), len(p['coords1'])) for p in pairs]
+    return coords, xyz, desc, sizes

@@ -30,6 +30,8 @@ typedef struct CUstream_st* eyoc_stream_t; /* == cudaStream_t */
 int eyoc_version(void);
 const char* eyoc_last_error(void);
 int eyoc_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+/* number of kernels this library has launched in this process (bench.py reports it as gpu_launches) */
+unsigned long long eyoc_launch_count(void);
 
 /* ---------------------------------------------------------------- nearest neighbour matching
  * Replaces lib/eval.py:18-48 find_nn_gpu (+ lib/metrics.py:26-27 pdist 'SquareL2')  [form 0]
