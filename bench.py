@@ -181,7 +181,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from eyoc_b200 import _C, nn as enn, synth
-    from eyoc_b200.pipeline import RegistrationPipeline, gather_records, plan_to_device
+    from eyoc_b200.pipeline import PlanPrefetcher, RegistrationPipeline, gather_records, plan_to_device
     from eyoc_b200.scripts.SC2_PCR.SC2_PCR import Matcher
     from eyoc_b200.scripts.test_kitti import is_success, rte_rre
 
@@ -194,6 +194,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     lib = _C.lib()
+    if args.conv_mode:
+        enn.CONV_MODE = args.conv_mode
     P = args.pairs_per_gpu
     K, W = args.steps, max(args.warmup, 3)
     pairs = synth.make_pairs(list(range(rank * P, rank * P + P)))
@@ -218,10 +220,12 @@ def run_ours(args):
         rec = pipe.records(out, list(range(rank * P, rank * P + P)))
         return gather_records(rec, P * world), out
 
+    prefetch = PlanPrefetcher(pipe, (sizes for _ in range(K + 2)))         # host RNG planning of block i+1 overlaps block i
+
     def step_e2e():
         c = coords_h.to(dev, non_blocking=True)
         x = xyz_h.to(dev, non_blocking=True)
-        out = pipe.run(c, x, sizes, plan=None, descriptors=desc_d)       # plan=None: host RNG draws + composition now
+        out = pipe.run(c, x, sizes, plan=prefetch.get(), descriptors=desc_d)   # fresh host RNG draws every step
         rec = pipe.records(out, list(range(rank * P, rank * P + P)))
         allrec = gather_records(rec, P * world)
         rec_host.copy_(allrec[rank * P: rank * P + P] if world > 1 else allrec, non_blocking=True)
@@ -262,6 +266,7 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
+    prefetch.close()
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -271,13 +276,23 @@ def run_ours(args):
     # ---- roofline of the sparse-conv gather-GEMM kernels (events recorded inside the timed region)
     m_cache, tot_ms, tot_bytes, tot_flops, n_tiled = {}, 0.0, 0, 0, 0
     for e0, e1, meta in prof:
-        if meta['cin'] % 32 or meta['cout'] % 32:
+        if meta['cin'] % 32 or meta['cout'] % 32 or meta['K'] > 32:
             continue                                            # conv1 (1->32) runs on the generic kernel
         b, f = conv_algorithmic_bytes(meta, m_cache)
         tot_ms += e0.elapsed_time(e1)
         tot_bytes += b
         tot_flops += f
         n_tiled += 1
+    if args.conv_breakdown and rank == 0:
+        per = {}
+        for e0, e1, meta in prof:
+            b, f = conv_algorithmic_bytes(meta, m_cache)
+            key = (meta['K'], meta['cin'], meta['cout'], meta['n_out'], meta['residual'])
+            d = per.setdefault(key, [0, 0.0, 0, 0])
+            d[0] += 1; d[1] += e0.elapsed_time(e1); d[2] += b; d[3] += f
+        for key, d in sorted(per.items(), key=lambda kv: -kv[1][1]):
+            print(f'conv K={key[0]:3d} cin={key[1]:3d} cout={key[2]:3d} n_out={key[3]:8d} res={int(key[4])} launches={d[0]:3d} '
+                  f'ms/launch={d[1] / d[0]:8.3f} algGB/s={d[2] / d[1] / 1e6:8.1f} TFLOP/s={d[3] / d[1] / 1e9:7.2f}', file=sys.stderr)
     peak, peak_src = _peaks()
     achieved = tot_bytes / (tot_ms / 1e3) / 1e9 if tot_ms > 0 else 0.0
     roofline = {'bound': 'hbm', 'kernel': 'sparse_conv_tiled_kernel (all tiled conv launches of the timed region)',
@@ -300,7 +315,7 @@ def run_ours(args):
                     + ('; estimator fed planted descriptors (the forward pass still runs and is timed)' if desc_d is not None else ''),
             'config': {'workload': WORKLOAD, 'pairs_per_gpu': P, 'global_pairs': P * world, 'voxels_per_step_per_gpu': int(coords_np.shape[0]),
                        'parallelism': f'pair-sharded x{world}', 'l2': 'per-step working set (>= 1 GB of level-1 features) exceeds the 126 MB L2; no explicit flush',
-                       'value_mode': 'coordinates, points and index plans resident in HBM'},
+                       'value_mode': 'coordinates, points and index plans resident in HBM', 'conv_mode': enn.CONV_MODE},
             'e2e': {'value': e2e, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(coords_np.nbytes + xyz_np.nbytes + 2 * 8 * P * 8000 + 2 * 8 * P * 5000),
                     'd2h_bytes_per_step': int(rec_host.numel() * 4), 'ms_per_step': 1e3 * e2e_s / K},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
@@ -323,8 +338,10 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--pairs-per-gpu', type=int, default=64)
     ap.add_argument('--descriptors', default='planted', choices=['planted', 'network'])
+    ap.add_argument('--conv-mode', default=None, choices=['fp32', 'tf32x3'])
     ap.add_argument('--cpu-pairs', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--conv-breakdown', action='store_true')
     args = ap.parse_args()
     if args.gpus > 1 and 'RANK' not in os.environ:        # convenience: self-launch one rank per GPU
         os.execvp(sys.executable, [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',

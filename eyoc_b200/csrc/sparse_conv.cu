@@ -175,6 +175,55 @@ sparse_conv_generic_kernel(ConvArgs a) {
     }
 }
 
+// First layer of the network (conv1: C_in = 1, K = 125, C_out = 32; model/resunet.py:31-37).  lane = output row, so
+// the K neighbour-table reads are coalesced; W (K x 32 floats) sits in shared memory and is read by broadcast; each
+// thread keeps its 32 output channels in registers and writes one full 128-byte row.
+template <int COUT>
+__global__ void __launch_bounds__(128)
+sparse_conv_cin1_kernel(ConvArgs a) {
+    extern __shared__ float wsm[];                    // [K][COUT]
+    for (int e = threadIdx.x; e < a.K * COUT; e += 128) wsm[e] = a.weight[e];
+    __syncthreads();
+    const int r0 = blockIdx.x * 128 + threadIdx.x;
+    if (r0 >= a.n_out) return;
+    const int r = a.row_perm ? a.row_perm[r0] : r0;
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+    for (int k = 0; k < a.K; ++k) {
+        const int v = a.nbr ? __ldg(a.nbr + (size_t)k * a.n_out + r) : r;
+        if (v < 0) continue;
+        const float x = __ldg(a.in0 + v);
+        const float4* w4 = reinterpret_cast<const float4*>(wsm + k * COUT);
+#pragma unroll
+        for (int c = 0; c < COUT / 4; ++c) {
+            const float4 w = w4[c];
+            acc[4 * c + 0] = __fmaf_rn(x, w.x, acc[4 * c + 0]);
+            acc[4 * c + 1] = __fmaf_rn(x, w.y, acc[4 * c + 1]);
+            acc[4 * c + 2] = __fmaf_rn(x, w.z, acc[4 * c + 2]);
+            acc[4 * c + 3] = __fmaf_rn(x, w.w, acc[4 * c + 3]);
+        }
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) {
+        float y = acc[c];
+        if (a.scale) y = __fmaf_rn(y, __ldg(a.scale + c), a.shift ? __ldg(a.shift + c) : 0.f);
+        else if (a.shift) y += __ldg(a.shift + c);
+        if (a.residual) y += a.residual[(size_t)r * COUT + c];
+        if (a.relu) y = fmaxf(y, 0.f);
+        ss = __fmaf_rn(y, y, ss);
+        acc[c] = y;
+    }
+    const float nrm = a.l2norm ? sqrtf(ss) : 1.f;
+#pragma unroll
+    for (int c = 0; c < COUT; c += 4) {
+        float4 y = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+        if (a.l2norm) { y.x = __fdiv_rn(y.x, nrm); y.y = __fdiv_rn(y.y, nrm); y.z = __fdiv_rn(y.z, nrm); y.w = __fdiv_rn(y.w, nrm); }
+        *reinterpret_cast<float4*>(a.out + (size_t)r * COUT + c) = y;
+    }
+}
+
 }  // namespace
 
 extern "C" int eyoc_sparse_conv(const float* in0, int c0, const float* in1, int c1, const int32_t* nbr, int K, int64_t n_out,
@@ -198,6 +247,8 @@ extern "C" int eyoc_sparse_conv(const float* in0, int c0, const float* in1, int 
             if (l2norm) EYOC_CHECK_ARG(cout == 32, "eyoc_sparse_conv: l2norm needs the row in one tile");
             sparse_conv_tiled_kernel<32, 4><<<dim3(gx, cout / 32), NT, 0, stream>>>(a);
         }
+    } else if (cin == 1 && cout == 32 && (size_t)K * 32 * 4 <= 48 * 1024) {
+        sparse_conv_cin1_kernel<32><<<(unsigned)((n_out + 127) / 128), 128, (size_t)K * 32 * 4, stream>>>(a);
     } else {
         EYOC_CHECK_ARG(!l2norm || cout <= 32, "eyoc_sparse_conv: l2norm on the generic path needs cout <= 32");
         sparse_conv_generic_kernel<<<(unsigned)((n_out + NT / 32 - 1) / (NT / 32)), NT, 0, stream>>>(a);

@@ -90,6 +90,31 @@ class MinkowskiBatchNorm(nn.Module):
                             coordinate_manager=x.coordinate_manager)
 
 
+# Data path of the convolutions that qualify (C_in multiple of 32, C_out in {32,64,128,256}, K <= 27):
+#   'tf32x3' : tcgen05 tensor cores, 3-term TF32 split, fp32 accumulation in TMEM (csrc/sparse_conv_tc.cu)
+#   'fp32'   : fp32 FMA register-tile kernel (csrc/sparse_conv.cu); also the path of everything that does not qualify
+CONV_MODE = 'tf32x3'
+_SPLIT_CACHE = {}
+
+
+def _split_weights(weight):
+    """[K, cin, cout] -> (wt_hi, wt_lo) [K, cout, cin], cached per parameter version."""
+    key = (weight.data_ptr(), int(weight._version), tuple(weight.shape), weight.device)
+    hit = _SPLIT_CACHE.get(key)
+    if hit is None:
+        w3 = weight if weight.dim() == 3 else weight[None]
+        K, cin, cout = w3.shape
+        hi = torch.empty((K, cout, cin), dtype=torch.float32, device=weight.device)
+        lo = torch.empty_like(hi)
+        with torch.cuda.device(weight.device):
+            _C.check(_C.lib().eyoc_conv_split_weights(_C.ptr(w3.contiguous()), _C.c_int(K), _C.c_int(cin), _C.c_int(cout),
+                                                      _C.ptr(hi), _C.ptr(lo), _C.stream()))
+        if len(_SPLIT_CACHE) > 256:
+            _SPLIT_CACHE.clear()
+        hit = _SPLIT_CACHE[key] = (hi, lo)
+    return hit
+
+
 # When set to a list, every sparse_conv_raw call appends (start_event, end_event, meta) - bench.py uses it to time
 # the convolution kernels with CUDA events on the launching stream inside the timed region.
 PROFILE = None
@@ -118,6 +143,15 @@ def _sparse_conv_call(in0, in1, nbr, weight, scale, shift, residual, relu, l2nor
     if weight.shape[-2] != c0 + c1:
         raise RuntimeError(f'kernel expects {weight.shape[-2]} input channels, got {c0}+{c1}')
     n_out = out.shape[0]
+    lib = _C.lib()
+    if CONV_MODE == 'tf32x3' and lib.eyoc_sparse_conv_tc_supported(c0, c1, cout, K, int(l2norm)):
+        hi, lo = _split_weights(weight)
+        with torch.cuda.device(in0.device):
+            _C.check(lib.eyoc_sparse_conv_tc(_C.ptr(in0), _C.c_int(c0), _C.ptr(in1), _C.c_int(c1), _C.ptr(nbr), _C.c_int(K),
+                                             _C.c_int64(n_out), _C.ptr(row_perm), _C.ptr(hi), _C.ptr(lo), _C.ptr(scale),
+                                             _C.ptr(shift), _C.ptr(residual), _C.c_int(int(relu)), _C.c_int(int(l2norm)),
+                                             _C.ptr(out), _C.c_int(cout), _C.stream()))
+        return out
     with torch.cuda.device(in0.device):
         _C.check(_C.lib().eyoc_sparse_conv(_C.ptr(in0), _C.c_int(c0), _C.ptr(in1), _C.c_int(c1), _C.ptr(nbr), _C.c_int(K),
                                            _C.c_int64(n_out), _C.ptr(row_perm), _C.ptr(weight), _C.ptr(scale),

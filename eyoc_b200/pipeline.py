@@ -138,6 +138,38 @@ class RegistrationPipeline:
         return rec
 
 
+class PlanPrefetcher:
+    """Runs ``pipe.plan(sizes)`` (the host RNG draws + index composition of the next block) on a worker thread so it
+    overlaps the GPU work of the current block.  Plans come out in the order they were drawn, so the global numpy
+    RNG stream is consumed exactly as by a sequential loop."""
+
+    def __init__(self, pipe, sizes_iter, depth=2):
+        import queue
+        import threading
+        self.q = queue.Queue(maxsize=depth)
+        self._stop = False
+
+        def work():
+            for sizes in sizes_iter:
+                if self._stop:
+                    break
+                self.q.put(pipe.plan(sizes))
+            self.q.put(None)
+        self.t = threading.Thread(target=work, daemon=True)
+        self.t.start()
+
+    def get(self):
+        return self.q.get()
+
+    def close(self):
+        self._stop = True
+        try:
+            while self.q.get_nowait() is not None:
+                pass
+        except Exception:
+            pass
+
+
 def gather_records(rec, num_pairs, group=None):
     """The path's only collective: ONE all-gather of the per-pair records.  Every rank pads its block to
     ceil(num_pairs / world) rows (block sizes follow from ``shard_range``, so no size exchange is needed);

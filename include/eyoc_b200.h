@@ -122,6 +122,16 @@ int eyoc_sparse_conv(const float* in0, int c0, const float* in1, int c1, const i
                      const int32_t* row_perm, const float* weight, const float* scale, const float* shift,
                      const float* residual, int relu, int l2norm, float* out, int cout, eyoc_stream_t stream);
 
+/* Tensor-core data path of the same operator (tcgen05.mma kind::tf32 with the 3-term hi/lo split, accumulators in
+ * TMEM).  Weights must first be split and transposed once: weight [K, cin, cout] -> wt_hi, wt_lo [K, cout, cin].
+ * Supported when eyoc_sparse_conv_tc_supported() returns 1 (cin, c0 multiples of 32; cout in {32,64,128,256}; K <= 32). */
+int eyoc_conv_split_weights(const float* weight, int K, int cin, int cout, float* wt_hi, float* wt_lo, eyoc_stream_t stream);
+int eyoc_sparse_conv_tc_supported(int c0, int c1, int cout, int K, int l2norm);
+int eyoc_sparse_conv_tc(const float* in0, int c0, const float* in1, int c1, const int32_t* nbr, int K, int64_t n_out,
+                        const int32_t* row_perm, const float* wt_hi, const float* wt_lo, const float* scale,
+                        const float* shift, const float* residual, int relu, int l2norm, float* out, int cout,
+                        eyoc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

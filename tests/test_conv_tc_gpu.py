@@ -1,0 +1,109 @@
+"""GPU: tensor-core sparse convolution (csrc/sparse_conv_tc.cu, tcgen05 TF32x3) vs the fp32 FMA kernel and an fp64
+gather-GEMM restatement, shape by shape, then the whole ResUNetBN2C forward vs the oracle in tf32x3 mode."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(in0, in1, nbr, W, scale, shift, residual, relu, l2norm):
+    x = in0 if in1 is None else torch.cat([in0, in1], 1)
+    x = x.double()
+    W3 = (W if W.dim() == 3 else W[None]).double()
+    n_out = nbr.shape[1] if nbr is not None else x.shape[0]
+    out = torch.zeros((n_out, W3.shape[-1]), dtype=torch.float64, device=x.device)
+    for k in range(W3.shape[0]):
+        if nbr is None:
+            out += x @ W3[k]
+        else:
+            idx = nbr[k].long()
+            m = idx >= 0
+            out[m] += x[idx[m]] @ W3[k]
+    if scale is not None:
+        out = out * scale.double() + shift.double()
+    elif shift is not None:
+        out = out + shift.double()
+    if residual is not None:
+        out = out + residual.double()
+    if relu:
+        out = out.clamp(min=0)
+    if l2norm:
+        out = out / out.norm(dim=1, keepdim=True)
+    return out
+
+
+@pytest.mark.parametrize('c0,c1,cout,K,n_in,n_out,opts', [
+    (32, 0, 32, 27, 700, 700, dict(bn=True, relu=True)),
+    (32, 0, 64, 27, 900, 300, dict(bn=True)),
+    (64, 0, 64, 27, 1500, 1500, dict(bn=True, residual=True, relu=True)),
+    (128, 0, 128, 27, 400, 400, dict(bn=True, relu=True)),
+    (128, 0, 256, 27, 500, 150, dict(bn=True)),
+    (256, 0, 256, 27, 130, 130, dict(bn=True, residual=True, relu=True)),
+    (256, 0, 128, 27, 130, 600, dict(bn=True, perm=True)),
+    (128, 128, 64, 27, 300, 1000, dict(bn=True, perm=True)),
+    (64, 32, 64, 1, 1000, 1000, dict(relu=True)),
+    (64, 0, 32, 1, 1000, 1000, dict(bias=True, l2norm=True)),
+    (64, 0, 64, 27, 5000, 40000, dict(bn=True, relu=True)),          # many tiles: nacc > 1 accumulators per CTA
+])
+def test_tc_conv_matches_fp32_and_fp64(c0, c1, cout, K, n_in, n_out, opts):
+    from eyoc_b200 import nn as enn
+    g = torch.Generator().manual_seed(c0 * 7 + cout + K + n_out)
+    dev = 'cuda'
+    in0 = torch.randn(n_in, c0, generator=g).to(dev)
+    in1 = torch.randn(n_in, c1, generator=g).to(dev) if c1 else None
+    cin = c0 + c1
+    W = (torch.randn((K, cin, cout) if K > 1 else (cin, cout), generator=g) / np.sqrt(cin * K)).to(dev)
+    nbr = None
+    if K > 1:
+        nbr = torch.randint(0, n_in, (K, n_out), generator=g, dtype=torch.int32)
+        nbr[torch.rand(K, n_out, generator=g) < 0.6] = -1
+        nbr[13] = torch.randint(0, n_in, (n_out,), generator=g, dtype=torch.int32)      # centre offset always present
+        nbr[5] = -1                                                                       # an offset nobody has
+        nbr = nbr.to(dev)
+    scale = shift = residual = perm = None
+    if opts.get('bn'):
+        scale = (torch.rand(cout, generator=g) + 0.5).to(dev)
+        shift = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    if opts.get('bias'):
+        shift = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    if opts.get('residual'):
+        residual = torch.randn(n_out, cout, generator=g).to(dev)
+    if opts.get('perm'):
+        perm = torch.randperm(n_out, generator=g).to(torch.int32).to(dev)
+    relu, l2 = bool(opts.get('relu')), bool(opts.get('l2norm'))
+    want = _ref(in0, in1, nbr, W, scale, shift, residual, relu, l2)
+    outs = {}
+    for mode in ('fp32', 'tf32x3'):
+        enn.CONV_MODE = mode
+        out = torch.full((n_out, cout), float('nan'), device=dev)
+        enn.sparse_conv_raw(in0, in1, nbr, W, scale, shift, residual, relu, l2, out, row_perm=perm)
+        torch.cuda.synchronize()
+        outs[mode] = out
+    enn.CONV_MODE = 'fp32'
+    scale_ref = float(want.abs().max())
+    e32 = float((outs['fp32'].double() - want).abs().max()) / scale_ref
+    etc = float((outs['tf32x3'].double() - want).abs().max()) / scale_ref
+    assert e32 < 5e-6, e32
+    assert etc < 1.5e-5, (etc, e32)          # 3xTF32: ~2^-18 relative, a few times the fp32 kernel
+
+
+def test_forward_tf32x3_vs_oracle():
+    from eyoc_b200 import nn as enn
+    from eyoc_b200.model import load_model
+    from eyoc_b200.sparse import SparseTensor
+    from oracle import resunet_oracle as RO
+    from tests.test_resunet_gpu import _cloud
+    coords = _cloud(3000, 4, batch=2)
+    feats = torch.ones((len(coords), 1), dtype=torch.float32)
+    sd = RO.make_state_dict(1, 32, 5, seed=4)
+    model = load_model('ResUNetBN2C')(1, 32, bn_momentum=0.05, normalize_feature=True, conv1_kernel_size=5, D=3)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    want = RO.resunet_forward(coords, feats, sd, True, 5)
+    try:
+        enn.CONV_MODE = 'tf32x3'
+        got = model(SparseTensor(feats.cuda(), coordinates=torch.from_numpy(coords).cuda())).F.cpu()
+    finally:
+        enn.CONV_MODE = 'fp32'
+    assert float((got - want).abs().max()) <= 1e-5, float((got - want).abs().max())
