@@ -196,6 +196,8 @@ def run_ours(args):
     lib = _C.lib()
     if args.conv_mode:
         enn.CONV_MODE = args.conv_mode
+    if args.no_tile_order:
+        enn.TILE_ORDER = False
     P = args.pairs_per_gpu
     K, W = args.steps, max(args.warmup, 3)
     pairs = synth.make_pairs(list(range(rank * P, rank * P + P)))
@@ -315,7 +317,7 @@ def run_ours(args):
                     + ('; estimator fed planted descriptors (the forward pass still runs and is timed)' if desc_d is not None else ''),
             'config': {'workload': WORKLOAD, 'pairs_per_gpu': P, 'global_pairs': P * world, 'voxels_per_step_per_gpu': int(coords_np.shape[0]),
                        'parallelism': f'pair-sharded x{world}', 'l2': 'per-step working set (>= 1 GB of level-1 features) exceeds the 126 MB L2; no explicit flush',
-                       'value_mode': 'coordinates, points and index plans resident in HBM', 'conv_mode': enn.CONV_MODE},
+                       'value_mode': 'coordinates, points and index plans resident in HBM', 'conv_mode': enn.CONV_MODE, 'tile_order': bool(enn.TILE_ORDER)},
             'e2e': {'value': e2e, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(coords_np.nbytes + xyz_np.nbytes + 2 * 8 * P * 8000 + 2 * 8 * P * 5000),
                     'd2h_bytes_per_step': int(rec_host.numel() * 4), 'ms_per_step': 1e3 * e2e_s / K},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
@@ -342,6 +344,7 @@ def main():
     ap.add_argument('--cpu-pairs', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--conv-breakdown', action='store_true')
+    ap.add_argument('--no-tile-order', action='store_true')
     args = ap.parse_args()
     if args.gpus > 1 and 'RANK' not in os.environ:        # convenience: self-launch one rank per GPU
         os.execvp(sys.executable, [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',

@@ -10,6 +10,7 @@
 // All of it is integer work bounded by HBM/L2 latency; lookups are one probe sequence per (k, o) with
 // coalesced writes along o.
 #include "common.cuh"
+#include <cub/device/device_radix_sort.cuh>
 #include "../../include/eyoc_b200.h"
 
 namespace {
@@ -65,6 +66,11 @@ __global__ void hash_build_kernel(const int* __restrict__ coords, int n, unsigne
     const int4 c = reinterpret_cast<const int4*>(coords)[i];
     if (!(c.x >= 0 && c.x <= 65535 && in_range16(c.y) && in_range16(c.z) && in_range16(c.w))) { atomicOr(status, 1); return; }
     hash_insert_min(keys, vals, cap, pack4(c.x, c.y, c.z, c.w), i);
+    // status[1] = largest batch index (one atomic per warp)
+    int b = c.x;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b = max(b, __shfl_xor_sync(__activemask(), b, o));
+    if ((threadIdx.x & 31) == 0 || i == 0) atomicMax(status + 1, b);
 }
 
 __global__ void hash_check_unique_kernel(const int* __restrict__ coords, int n, const unsigned long long* keys, const int* vals,
@@ -204,7 +210,65 @@ __global__ void parity_class_kernel(const int* __restrict__ coords, int n, int t
     cls[i] = (((c.y / ts) & 1)) | (((c.z / ts) & 1) << 1) | (((c.w / ts) & 1) << 2);
 }
 
+// Tile-order key of an output row: (cloud group << 27) | bit mask of the kernel offsets that have a neighbour.
+// Rows sorted by this key put rows with the same neighbour pattern into the same 128-row tile, so most
+// (tile, offset) items of the tensor-core convolution are either skipped or densely filled, while a group of
+// clouds (the L2 working set of the gather) stays contiguous.
+__global__ void tile_key_kernel(const int* __restrict__ nbr, int K, int n_out, const int* __restrict__ coords, int group,
+                                unsigned long long* __restrict__ keys, int* __restrict__ iota) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_out) return;
+    unsigned int m = 0;
+    for (int k = 0; k < K; ++k) m |= (unsigned int)(__ldg(nbr + (size_t)k * n_out + o) >= 0) << k;
+    const int b = coords[4 * (size_t)o];
+    keys[o] = ((unsigned long long)(unsigned int)(b / group) << 27) | m;
+    iota[o] = o;
+}
+
+__global__ void permute_columns_kernel(const int* __restrict__ nbr, int n_out, const int* __restrict__ perm, int* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    const size_t k = blockIdx.y;
+    out[k * n_out + i] = __ldg(nbr + k * n_out + __ldg(perm + i));
+}
+
 }  // namespace
+
+extern "C" size_t eyoc_tile_order_workspace_bytes(int64_t n_out) {
+    size_t temp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const int*)nullptr,
+                                    (int*)nullptr, (int)n_out, 0, 43);
+    return 2 * eyoc_align((size_t)n_out * 8) + eyoc_align((size_t)n_out * 4) + eyoc_align(temp) + 256;
+}
+
+extern "C" int eyoc_tile_order(const int32_t* nbr, int K, int64_t n_out, const int32_t* out_coords, int group_clouds, int max_batch,
+                               int32_t* row_perm, int32_t* nbr_tiled, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    EYOC_CHECK_ARG(nbr && out_coords && row_perm && nbr_tiled, "eyoc_tile_order: null argument");
+    EYOC_CHECK_ARG(K >= 1 && K <= 27 && group_clouds >= 1 && max_batch >= 0 && max_batch <= 65535, "eyoc_tile_order: bad K / group / batch");
+    EYOC_CHECK_ARG(n_out >= 0 && n_out < (1ll << 31), "eyoc_tile_order: bad n_out");
+    if (n_out == 0) return EYOC_OK;
+    if (workspace == nullptr || workspace_bytes < eyoc_tile_order_workspace_bytes(n_out)) {
+        eyoc_set_error("eyoc_tile_order: workspace too small");
+        return EYOC_ERR_WORKSPACE;
+    }
+    WsCarver c(workspace, workspace_bytes);
+    unsigned long long* keys = c.take<unsigned long long>(n_out);
+    unsigned long long* keys2 = c.take<unsigned long long>(n_out);
+    int* iota = c.take<int>(n_out);
+    size_t temp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp, keys, keys2, iota, row_perm, (int)n_out, 0, 43);
+    void* tmp = c.take<char>(temp);
+    const unsigned g = (unsigned)((n_out + 255) / 256);
+    tile_key_kernel<<<g, 256, 0, stream>>>(nbr, K, (int)n_out, out_coords, group_clouds, keys, iota);
+    EYOC_LAUNCH_CHECK();
+    int gbits = 0;
+    while ((max_batch / group_clouds) >> gbits) ++gbits;
+    EYOC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, temp, keys, keys2, iota, row_perm, (int)n_out, 0, 27 + gbits, stream));
+    g_eyoc_launches += 4;
+    permute_columns_kernel<<<dim3(g, K), 256, 0, stream>>>(nbr, (int)n_out, row_perm, nbr_tiled);
+    EYOC_LAUNCH_CHECK();
+    return EYOC_OK;
+}
 
 extern "C" int eyoc_hash_build(const int32_t* coords, int64_t n, uint64_t* table_keys, int32_t* table_vals, int64_t capacity,
                                int32_t* status, cudaStream_t stream) {

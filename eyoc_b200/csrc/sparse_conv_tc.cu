@@ -4,11 +4,14 @@
 // residual + ME.cat + L2 norm of model/resunet.py:142-193), different data path:
 //   * one CTA owns up to 8 accumulator tiles of 128 output rows x N = C_out channels, all resident in TMEM
 //     (512 columns x 128 lanes x fp32), so a W[k] slab staged in shared memory is reused by up to 1024 rows;
-//   * 4 producer warps gather the input rows of one (tile, kernel offset, 32-channel chunk) straight into the
-//     SWIZZLE_128B K-major UMMA layout (8 lanes cover one 128-byte row chunk: coalesced loads, conflict-free stores);
+//   * producer groups of 4 warps gather the input rows of one (tile, kernel offset, 32-channel chunk) straight into
+//     the SWIZZLE_128B K-major UMMA layout (8 lanes cover one 128-byte row chunk: coalesced loads, conflict-free
+//     st.shared.v4); the gather of a group's NEXT item is in flight while it splits and stores the current one;
+//   * weight slabs are pre-split and pre-swizzled once (eyoc_conv_split_weights) so that one TMA bulk copy
+//     (cp.async.bulk) per (offset, chunk) drops the exact shared-memory image, completion on an mbarrier;
 //   * 1 thread issues tcgen05.mma.kind::tf32; fp32-level accuracy comes from the 3-term split
 //     x = hi + lo (both rounded to tf32):  A_hi W_hi + A_hi W_lo + A_lo W_hi  accumulated in fp32 in TMEM;
-//   * smem ring (A) / double buffer (W) hand-shaken with mbarriers, slots released by tcgen05.commit;
+//   * smem ring (A) / ring (W) hand-shaken with mbarriers, slots released by tcgen05.commit;
 //   * the producer warps become the epilogue: tcgen05.ld 32 lanes x 16 columns, fused affine / residual / ReLU /
 //     L2 norm, one output row per thread.
 // Kernel offsets (and whole W slabs) with no neighbour in a tile are skipped by both sides from a shared bit mask.
@@ -20,8 +23,6 @@ namespace {
 constexpr int UM = 128;        // rows per accumulator tile (UMMA M)
 constexpr int KC = 32;         // channels per chunk = one 128-byte swizzle-atom row of fp32
 constexpr int MAXACC = 8;
-constexpr int NPROD = 128;     // producer / epilogue threads
-constexpr int NTHREADS = NPROD + 32;
 constexpr int A_BYTES = UM * KC * 4;   // 16 KB per (hi | lo) tile
 
 // ------------------------------------------------------------------------------------------- PTX wrappers
@@ -78,6 +79,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared (1-D), completion counted on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// x = hi + lo with hi = x rounded to tf32 (round-to-nearest, ties away = cvt.rna.tf32.f32 for finite x: add half an
+// ulp of the 10-bit mantissa to the magnitude, clear the 13 low bits), lo = tf32(x - hi) the same way.  Two integer
+// ops per rounding instead of the four-instruction sequence ptxas emits for cvt.rna (Inf/NaN guard).
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
+}
 __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -98,19 +117,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 struct TcArgs {
     const float* in0; int c0;
     const float* in1; int c1;
-    const int32_t* nbr;
-    const int32_t* row_perm;
-    const float* wt_hi;       // [K, cout, cin] tf32-rounded
-    const float* wt_lo;       // [K, cout, cin] tf32-rounded residual
+    const int32_t* nbr;       // [K, n_out]; column = output row, or tile position when nbr_tiled
+    const int32_t* row_perm;  // [n_out] tile position -> output row, or null
+    const float* wt_img;      // [K][cin/32][hi|lo][cout][32] swizzled shared-memory images (eyoc_conv_split_weights)
     const float* scale;
     const float* shift;
     const float* residual;
     float* out;
-    int K, n_out, relu, l2norm, nacc;
+    int K, n_out, relu, l2norm, nacc, nbr_tiled;
 };
 
 constexpr int MAX_ITEMS = 27 * 12 * MAXACC;      // (kernel offset, 32-channel chunk, tile) work items per CTA
-constexpr int NWLOAD = 64;                       // weight-slab loader threads
 
 // Work item: bits [0,5) kernel offset, [5,9) chunk index, [9,12) tile, bit 12 = first item of its (offset, chunk),
 // i.e. the MMA side must switch to the next weight slab.
@@ -119,21 +136,19 @@ __device__ __forceinline__ int item_c(uint32_t it) { return (it >> 5) & 15; }
 __device__ __forceinline__ int item_t(uint32_t it) { return (it >> 9) & 7; }
 __device__ __forceinline__ bool item_first(uint32_t it) { return (it >> 12) & 1; }
 
-// Thread map: NPG producer groups of 128 threads (group g owns A stage g), then NWLOAD weight-loader threads, then
-// one MMA-issuer warp.  Producers prefetch the gathered rows into registers BEFORE waiting for their smem slot, so
-// the L2 latency of a gather overlaps the MMAs of the group's previous item and the gathers of the other groups.
+// Thread map: NPG producer groups of 128 threads (group g owns A stage g), one weight-loader warp (TMA bulk copies,
+// one elected thread), one MMA-issuer warp (one elected thread).
 template <int N, int NPG, int NSW>
-__global__ void __launch_bounds__(NPG * 128 + NWLOAD + 32, 1)
+__global__ void __launch_bounds__(NPG * 128 + 64, 1)
 sparse_conv_tc_kernel(TcArgs a) {
     constexpr int W_BYTES = N * KC * 4;
     constexpr int NPT = NPG * 128;
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
     constexpr int TMEM_COLS = (MAXACC * N > 512) ? 512 : MAXACC * N;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = smem;                                   // NPG x (hi | lo)
-    uint8_t* sW = sA + NPG * 2 * A_BYTES;                 // NSW x (hi | lo)
-    int* idx_s = (int*)(sW + NSW * 2 * W_BYTES);          // [NPG][2][UM]
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = smem0;                                   // NPG x (hi | lo)
+    const uint32_t sW = sA + NPG * 2 * A_BYTES;                  // NSW x (hi | lo)
     __shared__ uint64_t bars[2 * NPG + 2 * NSW + 1];
     __shared__ uint32_t tmem_base_s;
     __shared__ uint32_t valid[MAXACC];
@@ -149,11 +164,11 @@ sparse_conv_tc_kernel(TcArgs a) {
     const uint32_t a_full = smem_u32(&bars[0]), a_empty = smem_u32(&bars[NPG]);
     const uint32_t w_full = smem_u32(&bars[2 * NPG]), w_empty = smem_u32(&bars[2 * NPG + NSW]);
     const uint32_t done_bar = smem_u32(&bars[2 * NPG + 2 * NSW]);
-    const int mma_warp = (NPT + NWLOAD) / 32;
+    const int wload_warp = NPT / 32, mma_warp = NPT / 32 + 1;
 
     if (tid == 0) {
         for (int i = 0; i < NPG; ++i) { mbar_init(a_full + 8 * i, 128); mbar_init(a_empty + 8 * i, 1); }
-        for (int i = 0; i < NSW; ++i) { mbar_init(w_full + 8 * i, NWLOAD); mbar_init(w_empty + 8 * i, 1); }
+        for (int i = 0; i < NSW; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
         mbar_init(done_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -170,15 +185,13 @@ sparse_conv_tc_kernel(TcArgs a) {
         const int r = tid & 127;
         for (int t = tid >> 7; t < nacc; t += NPG) {
             const int rr = (tile0 + t) * UM + r;
-            const int row = rr < a.n_out ? (a.row_perm ? a.row_perm[rr] : rr) : -1;
+            int col = -1;
+            if (rr < a.n_out) col = (a.row_perm && !a.nbr_tiled) ? a.row_perm[rr] : rr;
             uint32_t m = 0;
             if (a.nbr == nullptr) {
-                m = row >= 0 ? 1u : 0u;
-            } else {
-                for (int k = 0; k < a.K; ++k) {
-                    const int v = row >= 0 ? __ldg(a.nbr + (size_t)k * a.n_out + row) : -1;
-                    m |= (uint32_t)(v >= 0) << k;
-                }
+                m = col >= 0 ? 1u : 0u;
+            } else if (col >= 0) {
+                for (int k = 0; k < a.K; ++k) m |= (uint32_t)(__ldg(a.nbr + (size_t)k * a.n_out + col) >= 0) << k;
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
@@ -229,55 +242,70 @@ sparse_conv_tc_kernel(TcArgs a) {
 
     if (tid < NPT) {
         // =========================================================== producers: gather + tf32 split -> smem
-        const int g = tid >> 7, r128 = tid & 127, w4 = warp & 3;
-        const int c = lane & 7;
-        uint8_t* dh = sA + g * 2 * A_BYTES;
-        uint8_t* dl = dh + A_BYTES;
-        int* ixbase = idx_s + g * 2 * UM;
+        const int g = tid >> 7, w4 = warp & 3;
+        const int c = lane & 7, rsub = lane >> 3;
+        const uint32_t dh = sA + g * 2 * A_BYTES;
+        // row r = w4*32 + q*4 + rsub, 16-byte chunk c of its 128-byte line lands at r*128 + ((c ^ (r & 7)) << 4)
+        const uint32_t st0 = dh + (uint32_t)(w4 * 32 + rsub) * 128u + (uint32_t)((c ^ rsub) << 4);        // q even
+        const uint32_t st1 = dh + (uint32_t)(w4 * 32 + rsub) * 128u + (uint32_t)((c ^ rsub ^ 4) << 4);    // q odd
+        // lane l of the warp fetches the neighbour index of row w4*32 + l (coalesced); rows are handed out by shuffle
         auto load_idx = [&](uint32_t it) -> int {
-            const int rr = (tile0 + item_t(it)) * UM + r128;
+            const int rr = (tile0 + item_t(it)) * UM + w4 * 32 + lane;
             int v = -1;
             if (rr < a.n_out) {
-                const int row = a.row_perm ? a.row_perm[rr] : rr;
-                v = a.nbr ? __ldg(a.nbr + (size_t)item_k(it) * a.n_out + row) : row;
+                const int col = (a.row_perm && !a.nbr_tiled) ? __ldg(a.row_perm + rr) : rr;
+                v = a.nbr ? __ldg(a.nbr + (size_t)item_k(it) * a.n_out + col) : (a.row_perm ? __ldg(a.row_perm + rr) : rr);
             }
             return v;
         };
-        int i = g;
-        int vnext = i < nitems ? load_idx(items[i]) : -1;
-        uint32_t n = 0;
-        for (; i < nitems; i += NPG, ++n) {
-            const uint32_t it = items[i];
+        auto gather = [&](float4 (&x)[8], uint32_t it, int idx) {
             const int cc = item_c(it) * KC;
             const float* src = cc < a.c0 ? a.in0 : a.in1;
             const int cs = cc < a.c0 ? a.c0 : a.c1;
-            const int co = cc < a.c0 ? cc : cc - a.c0;
-            int* ix = ixbase + (n & 1u) * UM;
-            ix[r128] = vnext;
-            asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
-            float4 x[8];
+            const int co = (cc < a.c0 ? cc : cc - a.c0) + c * 4;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const int r = w4 * 32 + q * 4 + (lane >> 3);
-                const int v = ix[r];
+                const int v = __shfl_sync(0xffffffffu, idx, q * 4 + rsub);
                 x[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (v >= 0) x[q] = __ldg(reinterpret_cast<const float4*>(src + (size_t)v * cs + co + c * 4));
+                if (v >= 0) x[q] = __ldg(reinterpret_cast<const float4*>(src + (size_t)v * cs + co));
             }
-            if (i + NPG < nitems) vnext = load_idx(items[i + NPG]);
-            mbar_wait(a_empty + 8 * g, (n & 1u) ^ 1u);
+        };
+        auto split_store = [&](const float4 (&x)[8]) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const int r = w4 * 32 + q * 4 + (lane >> 3);
-                uint4 h, l;
-                h.x = to_tf32(x[q].x); h.y = to_tf32(x[q].y); h.z = to_tf32(x[q].z); h.w = to_tf32(x[q].w);
-                l.x = to_tf32(x[q].x - __uint_as_float(h.x)); l.y = to_tf32(x[q].y - __uint_as_float(h.y));
-                l.z = to_tf32(x[q].z - __uint_as_float(h.z)); l.w = to_tf32(x[q].w - __uint_as_float(h.w));
-                const int off = r * 128 + ((c ^ (r & 7)) << 4);
-                *reinterpret_cast<uint4*>(dh + off) = h;
-                *reinterpret_cast<uint4*>(dl + off) = l;
+                uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                split_tf32(x[q].x, h0, l0); split_tf32(x[q].y, h1, l1);
+                split_tf32(x[q].z, h2, l2); split_tf32(x[q].w, h3, l3);
+                const uint32_t addr = ((q & 1) ? st1 : st0) + (uint32_t)q * 512u;
+                sts128(addr, h0, h1, h2, h3);
+                sts128(addr + A_BYTES, l0, l1, l2, l3);
             }
+        };
+        // software pipeline per group: indices two items ahead, gathered rows one item ahead
+        float4 xa[8], xb[8];
+        int i = g;
+        int idx_a = i < nitems ? load_idx(items[i]) : -1;
+        int idx_b = i + NPG < nitems ? load_idx(items[i + NPG]) : -1;
+        if (i < nitems) gather(xa, items[i], idx_a);
+        uint32_t n = 0;
+        while (i < nitems) {
+            // ---- even step: xa is current, xb receives the next item
+            if (i + NPG < nitems) gather(xb, items[i + NPG], idx_b);
+            idx_a = i + 2 * NPG < nitems ? load_idx(items[i + 2 * NPG]) : -1;
+            mbar_wait(a_empty + 8 * g, (n & 1u) ^ 1u);
+            split_store(xa);
             fence_proxy_async();
             mbar_arrive(a_full + 8 * g);
+            i += NPG; ++n;
+            if (i >= nitems) break;
+            // ---- odd step: xb is current, xa receives the next item
+            if (i + NPG < nitems) gather(xa, items[i + NPG], idx_a);
+            idx_b = i + 2 * NPG < nitems ? load_idx(items[i + 2 * NPG]) : -1;
+            mbar_wait(a_empty + 8 * g, (n & 1u) ^ 1u);
+            split_store(xb);
+            fence_proxy_async();
+            mbar_arrive(a_full + 8 * g);
+            i += NPG; ++n;
         }
         // =========================================================== epilogue: TMEM -> registers -> global
         mbar_wait(done_bar, 0);
@@ -335,32 +363,22 @@ sparse_conv_tc_kernel(TcArgs a) {
             }
         }
         tc_fence_before();
-    } else if (tid < NPT + NWLOAD) {
-        // =========================================================== weight-slab loaders
-        const int wt = tid - NPT;
-        uint32_t w_it = 0;
-        for (int i = 0; i < nitems; ++i) {
-            const uint32_t it = items[i];
-            if (!item_first(it)) continue;
-            const int k = item_k(it), cc = item_c(it) * KC;
-            const uint32_t ws = w_it % NSW;
-            mbar_wait(w_empty + 8 * ws, ((w_it / NSW) & 1u) ^ 1u);
-            uint8_t* dh = sW + ws * 2 * W_BYTES;
-            uint8_t* dl = dh + W_BYTES;
-#pragma unroll 4
-            for (int e = wt; e < N * 8; e += NWLOAD) {
-                const int n = e >> 3, c = e & 7;
-                const size_t gofs = ((size_t)k * N + n) * cin + cc + c * 4;
-                const float4 h = __ldg(reinterpret_cast<const float4*>(a.wt_hi + gofs));
-                const float4 l = __ldg(reinterpret_cast<const float4*>(a.wt_lo + gofs));
-                const int off = n * 128 + ((c ^ (n & 7)) << 4);
-                *reinterpret_cast<float4*>(dh + off) = h;
-                *reinterpret_cast<float4*>(dl + off) = l;
+    } else if (warp == wload_warp) {
+        // =========================================================== weight slabs: one TMA bulk copy each
+        if (lane == 0) {
+            uint32_t w_it = 0;
+            for (int i = 0; i < nitems; ++i) {
+                const uint32_t it = items[i];
+                if (!item_first(it)) continue;
+                const uint32_t ws = w_it % NSW;
+                mbar_wait(w_empty + 8 * ws, ((w_it / NSW) & 1u) ^ 1u);
+                mbar_expect_tx(w_full + 8 * ws, 2 * W_BYTES);
+                bulk_g2s(sW + ws * 2 * W_BYTES, a.wt_img + ((size_t)item_k(it) * nch + item_c(it)) * (2 * N * KC), 2 * W_BYTES,
+                         w_full + 8 * ws);
+                ++w_it;
             }
-            fence_proxy_async();
-            mbar_arrive(w_full + 8 * ws);
-            ++w_it;
         }
+        __syncwarp();
     } else {
         // =========================================================== MMA issuer (one thread)
         uint32_t w_it = 0, started = 0;
@@ -371,7 +389,7 @@ sparse_conv_tc_kernel(TcArgs a) {
                 if (w_it > 0 && lane == 0) umma_commit(w_empty + 8 * ((w_it - 1) % NSW));   // previous slab fully consumed
                 const uint32_t ws = w_it % NSW;
                 mbar_wait(w_full + 8 * ws, (w_it / NSW) & 1u);
-                wh = smem_u32(sW + ws * 2 * W_BYTES);
+                wh = sW + ws * 2 * W_BYTES;
                 wl = wh + W_BYTES;
                 ++w_it;
             }
@@ -379,7 +397,7 @@ sparse_conv_tc_kernel(TcArgs a) {
             mbar_wait(a_full + 8 * g, (uint32_t)(i / NPG) & 1u);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t ah = smem_u32(sA + g * 2 * A_BYTES), al = ah + A_BYTES;
+                const uint32_t ah = sA + g * 2 * A_BYTES, al = ah + A_BYTES;
                 const uint32_t d = tmem_base + (uint32_t)(t * N);
                 uint32_t acc = (started >> t) & 1u;
 #pragma unroll
@@ -406,39 +424,43 @@ sparse_conv_tc_kernel(TcArgs a) {
     }
 }
 
-__global__ void split_weights_kernel(const float* __restrict__ w, int K, int cin, int cout, float* __restrict__ hi,
-                                     float* __restrict__ lo) {
+// weight [K, cin, cout] -> shared-memory images [K][cin/32][hi|lo][cout rows][32 channels], each row's eight 16-byte
+// chunks XOR-swizzled with (row & 7) exactly as the SWIZZLE_128B K-major UMMA descriptor expects them.
+__global__ void split_weights_kernel(const float* __restrict__ w, int K, int cin, int cout, float* __restrict__ img) {
     const size_t total = (size_t)K * cin * cout;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    // destination index runs over [K][cout][cin]
     const int c = (int)(i % cin);
     const int n = (int)((i / cin) % cout);
     const int k = (int)(i / ((size_t)cin * cout));
     const float x = w[((size_t)k * cin + c) * cout + n];
     const float h = __uint_as_float(to_tf32(x));
-    hi[i] = h;
-    lo[i] = __uint_as_float(to_tf32(x - h));
+    const float l = __uint_as_float(to_tf32(x - h));
+    const int ci = c / KC, cl = c % KC;
+    const size_t slab = ((size_t)k * (cin / KC) + ci) * (2 * (size_t)cout * KC);
+    const int off = n * KC + ((((cl >> 2) ^ (n & 7)) << 2) | (cl & 3));
+    img[slab + off] = h;
+    img[slab + (size_t)cout * KC + off] = l;
 }
 
 template <int N, int NPG, int NSW>
 int launch_tc(const TcArgs& a, cudaStream_t stream) {
-    const size_t smem = 1024 + (size_t)NPG * 2 * A_BYTES + (size_t)NSW * 2 * N * KC * 4 + (size_t)NPG * 2 * UM * 4;
+    const size_t smem = 1024 + (size_t)NPG * 2 * A_BYTES + (size_t)NSW * 2 * N * KC * 4;
     EYOC_CUDA(cudaFuncSetAttribute(sparse_conv_tc_kernel<N, NPG, NSW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = (a.n_out + UM - 1) / UM;
     const int grid = (tiles + a.nacc - 1) / a.nacc;
-    sparse_conv_tc_kernel<N, NPG, NSW><<<grid, NPG * 128 + NWLOAD + 32, smem, stream>>>(a);
+    sparse_conv_tc_kernel<N, NPG, NSW><<<grid, NPG * 128 + 64, smem, stream>>>(a);
     EYOC_LAUNCH_CHECK();
     return EYOC_OK;
 }
 
 }  // namespace
 
-extern "C" int eyoc_conv_split_weights(const float* weight, int K, int cin, int cout, float* wt_hi, float* wt_lo,
-                                       cudaStream_t stream) {
-    EYOC_CHECK_ARG(weight && wt_hi && wt_lo && K >= 1 && cin >= 1 && cout >= 1, "eyoc_conv_split_weights: bad argument");
+extern "C" int eyoc_conv_split_weights(const float* weight, int K, int cin, int cout, float* wt_img, cudaStream_t stream) {
+    EYOC_CHECK_ARG(weight && wt_img && K >= 1 && cin >= 1 && cout >= 1, "eyoc_conv_split_weights: bad argument");
+    EYOC_CHECK_ARG(cin % KC == 0, "eyoc_conv_split_weights: cin must be a multiple of 32");
     const size_t total = (size_t)K * cin * cout;
-    split_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(weight, K, cin, cout, wt_hi, wt_lo);
+    split_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(weight, K, cin, cout, wt_img);
     EYOC_LAUNCH_CHECK();
     return EYOC_OK;
 }
@@ -452,20 +474,21 @@ extern "C" int eyoc_sparse_conv_tc_supported(int c0, int c1, int cout, int K, in
 }
 
 extern "C" int eyoc_sparse_conv_tc(const float* in0, int c0, const float* in1, int c1, const int32_t* nbr, int K, int64_t n_out,
-                                   const int32_t* row_perm, const float* wt_hi, const float* wt_lo, const float* scale,
+                                   const int32_t* row_perm, int nbr_tiled, const float* wt_img, const float* scale,
                                    const float* shift, const float* residual, int relu, int l2norm, float* out, int cout,
                                    cudaStream_t stream) {
-    EYOC_CHECK_ARG(in0 && wt_hi && wt_lo && out, "eyoc_sparse_conv_tc: null argument");
+    EYOC_CHECK_ARG(in0 && wt_img && out, "eyoc_sparse_conv_tc: null argument");
     EYOC_CHECK_ARG((in1 != nullptr) == (c1 > 0), "eyoc_sparse_conv_tc: in1 and c1 must be given together");
     EYOC_CHECK_ARG(nbr || K == 1, "eyoc_sparse_conv_tc: a neighbour table is required when K > 1");
     EYOC_CHECK_ARG(eyoc_sparse_conv_tc_supported(c0, c1, cout, K, l2norm), "eyoc_sparse_conv_tc: unsupported shape c0=%d c1=%d cout=%d K=%d", c0, c1, cout, K);
     EYOC_CHECK_ARG(n_out >= 0 && n_out < (1ll << 31), "eyoc_sparse_conv_tc: bad n_out");
+    EYOC_CHECK_ARG(!nbr_tiled || row_perm, "eyoc_sparse_conv_tc: a tiled neighbour table needs row_perm");
     if (n_out == 0) return EYOC_OK;
     const int maxacc = cout <= 64 ? 8 : (cout == 128 ? 4 : 2);
     const int64_t tiles = (n_out + UM - 1) / UM;
     int nacc = (int)(tiles / (2 * 148));               // keep >= 2 CTAs per SM's worth of work before widening
     nacc = nacc < 1 ? 1 : (nacc > maxacc ? maxacc : nacc);
-    TcArgs a{in0, c0, in1, c1, nbr, row_perm, wt_hi, wt_lo, scale, shift, residual, out, K, (int)n_out, relu, l2norm, nacc};
+    TcArgs a{in0, c0, in1, c1, nbr, row_perm, wt_img, scale, shift, residual, out, K, (int)n_out, relu, l2norm, nacc, nbr_tiled};
     switch (cout) {
         case 32: return launch_tc<32, 4, 4>(a, stream);
         case 64: return launch_tc<64, 4, 4>(a, stream);

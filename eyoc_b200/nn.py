@@ -32,6 +32,15 @@ class MinkowskiConvolution(nn.Module):
         self.bias = nn.Parameter(torch.zeros((1, out_channels), dtype=torch.float32)) if bias else None
         self.reset_parameters()
 
+    def tc_image(self):
+        """Split / swizzled weight image of the tensor-core path, cached on the module per parameter version."""
+        k = self.kernel
+        ver = (int(k._version), k.data_ptr(), k.device)
+        cache = getattr(self, '_tc_image', None)
+        if cache is None or cache[0] != ver:
+            cache = self._tc_image = (ver, split_weights(k.detach()))
+        return cache[1]
+
     def reset_parameters(self):
         with torch.no_grad():
             n = self.in_channels * self.kernel_size ** 3
@@ -94,25 +103,20 @@ class MinkowskiBatchNorm(nn.Module):
 #   'tf32x3' : tcgen05 tensor cores, 3-term TF32 split, fp32 accumulation in TMEM (csrc/sparse_conv_tc.cu)
 #   'fp32'   : fp32 FMA register-tile kernel (csrc/sparse_conv.cu); also the path of everything that does not qualify
 CONV_MODE = 'tf32x3'
-_SPLIT_CACHE = {}
+# Tensor-core convolutions tile their output rows in (cloud group, neighbour pattern) order (CoordinateManager.tiled_map)
+TILE_ORDER = True
 
 
-def _split_weights(weight):
-    """[K, cin, cout] -> (wt_hi, wt_lo) [K, cout, cin], cached per parameter version."""
-    key = (weight.data_ptr(), int(weight._version), tuple(weight.shape), weight.device)
-    hit = _SPLIT_CACHE.get(key)
-    if hit is None:
-        w3 = weight if weight.dim() == 3 else weight[None]
-        K, cin, cout = w3.shape
-        hi = torch.empty((K, cout, cin), dtype=torch.float32, device=weight.device)
-        lo = torch.empty_like(hi)
-        with torch.cuda.device(weight.device):
-            _C.check(_C.lib().eyoc_conv_split_weights(_C.ptr(w3.contiguous()), _C.c_int(K), _C.c_int(cin), _C.c_int(cout),
-                                                      _C.ptr(hi), _C.ptr(lo), _C.stream()))
-        if len(_SPLIT_CACHE) > 256:
-            _SPLIT_CACHE.clear()
-        hit = _SPLIT_CACHE[key] = (hi, lo)
-    return hit
+def split_weights(weight):
+    """[K, cin, cout] (or [cin, cout]) -> wt_img [K, cin/32, 2, cout, 32]: tf32 hi | lo parts laid out as the
+    swizzled shared-memory images the tensor-core kernel copies with one TMA bulk copy per slab."""
+    w3 = weight if weight.dim() == 3 else weight[None]
+    K, cin, cout = w3.shape
+    img = torch.empty((K, cin // 32, 2, cout, 32), dtype=torch.float32, device=weight.device)
+    with torch.cuda.device(weight.device):
+        _C.check(_C.lib().eyoc_conv_split_weights(_C.ptr(w3.contiguous()), _C.c_int(K), _C.c_int(cin), _C.c_int(cout),
+                                                  _C.ptr(img), _C.stream()))
+    return img
 
 
 # When set to a list, every sparse_conv_raw call appends (start_event, end_event, meta) - bench.py uses it to time
@@ -120,21 +124,28 @@ def _split_weights(weight):
 PROFILE = None
 
 
-def sparse_conv_raw(in0, in1, nbr, weight, scale, shift, residual, relu, l2norm, out, row_perm=None):
-    """Thin call into eyoc_sparse_conv (include/eyoc_b200.h)."""
+def sparse_conv_raw(in0, in1, nbr, weight, scale, shift, residual, relu, l2norm, out, row_perm=None, nbr_tiled=False,
+                    wt_img=None):
+    """Thin call into eyoc_sparse_conv / eyoc_sparse_conv_tc (include/eyoc_b200.h).  nbr_tiled: the columns of ``nbr``
+    are already in ``row_perm`` order (CoordinateManager.tiled_map); wt_img: cached ``split_weights(weight)``."""
     if PROFILE is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        _sparse_conv_call(in0, in1, nbr, weight, scale, shift, residual, relu, l2norm, out, row_perm)
+        _sparse_conv_call(in0, in1, nbr, weight, scale, shift, residual, relu, l2norm, out, row_perm, nbr_tiled, wt_img)
         ev1.record()
         PROFILE.append((ev0, ev1, dict(K=1 if weight.dim() == 2 else weight.shape[0], cin=weight.shape[-2],
                                        cout=weight.shape[-1], n_out=out.shape[0], nbr=nbr,
                                        residual=residual is not None)))
         return out
-    return _sparse_conv_call(in0, in1, nbr, weight, scale, shift, residual, relu, l2norm, out, row_perm)
+    return _sparse_conv_call(in0, in1, nbr, weight, scale, shift, residual, relu, l2norm, out, row_perm, nbr_tiled, wt_img)
 
 
-def _sparse_conv_call(in0, in1, nbr, weight, scale, shift, residual, relu, l2norm, out, row_perm=None):
+def tc_supported(c0, c1, cout, K, l2norm):
+    return CONV_MODE == 'tf32x3' and bool(_C.lib().eyoc_sparse_conv_tc_supported(c0, c1, cout, K, int(l2norm)))
+
+
+def _sparse_conv_call(in0, in1, nbr, weight, scale, shift, residual, relu, l2norm, out, row_perm=None, nbr_tiled=False,
+                      wt_img=None):
     _C.require_cuda(in0, in1, nbr, weight, scale, shift, residual, out, row_perm)
     c0 = in0.shape[1]
     c1 = in1.shape[1] if in1 is not None else 0
@@ -144,14 +155,16 @@ def _sparse_conv_call(in0, in1, nbr, weight, scale, shift, residual, relu, l2nor
         raise RuntimeError(f'kernel expects {weight.shape[-2]} input channels, got {c0}+{c1}')
     n_out = out.shape[0]
     lib = _C.lib()
-    if CONV_MODE == 'tf32x3' and lib.eyoc_sparse_conv_tc_supported(c0, c1, cout, K, int(l2norm)):
-        hi, lo = _split_weights(weight)
+    if tc_supported(c0, c1, cout, K, l2norm):
+        img = wt_img if wt_img is not None else split_weights(weight)
         with torch.cuda.device(in0.device):
             _C.check(lib.eyoc_sparse_conv_tc(_C.ptr(in0), _C.c_int(c0), _C.ptr(in1), _C.c_int(c1), _C.ptr(nbr), _C.c_int(K),
-                                             _C.c_int64(n_out), _C.ptr(row_perm), _C.ptr(hi), _C.ptr(lo), _C.ptr(scale),
-                                             _C.ptr(shift), _C.ptr(residual), _C.c_int(int(relu)), _C.c_int(int(l2norm)),
-                                             _C.ptr(out), _C.c_int(cout), _C.stream()))
+                                             _C.c_int64(n_out), _C.ptr(row_perm), _C.c_int(int(nbr_tiled)), _C.ptr(img),
+                                             _C.ptr(scale), _C.ptr(shift), _C.ptr(residual), _C.c_int(int(relu)),
+                                             _C.c_int(int(l2norm)), _C.ptr(out), _C.c_int(cout), _C.stream()))
         return out
+    if nbr_tiled:
+        raise RuntimeError('a tiled neighbour table is only understood by the tensor-core convolution')
     with torch.cuda.device(in0.device):
         _C.check(_C.lib().eyoc_sparse_conv(_C.ptr(in0), _C.c_int(c0), _C.ptr(in1), _C.c_int(c1), _C.ptr(nbr), _C.c_int(K),
                                            _C.c_int64(n_out), _C.ptr(row_perm), _C.ptr(weight), _C.ptr(scale),
@@ -169,10 +182,16 @@ def conv_bn_act(x, conv, norm=None, residual=None, relu=False, l2norm=False, ski
     ts_out = conv.out_stride(ts_in)
     nbr = None
     row_perm = None
+    tiled = False
     if conv.kernel_size > 1 or ts_out != ts_in:
-        nbr = mgr.kernel_map(ts_in, ts_out, conv.kernel_size, transposed=conv.TRANSPOSED)
-        if conv.TRANSPOSED:
-            row_perm = mgr.parity_perm(ts_out)
+        c0_, c1_ = x.F.shape[1], (skip.F.shape[1] if skip is not None else 0)
+        if TILE_ORDER and tc_supported(c0_, c1_, conv.out_channels, conv.kernel_size ** 3, l2norm):
+            nbr, row_perm = mgr.tiled_map(ts_in, ts_out, conv.kernel_size, transposed=conv.TRANSPOSED)
+            tiled = True
+        else:
+            nbr = mgr.kernel_map(ts_in, ts_out, conv.kernel_size, transposed=conv.TRANSPOSED)
+            if conv.TRANSPOSED:
+                row_perm = mgr.parity_perm(ts_out)
     mgr.ensure_levels(max(ts_in, ts_out))
     n_out = mgr.num_rows(ts_out)
     scale = shift = None
@@ -188,7 +207,9 @@ def conv_bn_act(x, conv, norm=None, residual=None, relu=False, l2norm=False, ski
         in1 = skip.F if skip.F.is_contiguous() else skip.F.contiguous()
     out = torch.empty((n_out, conv.out_channels), dtype=torch.float32, device=in0.device)
     sparse_conv_raw(in0, in1, nbr, conv.kernel.detach(), scale, shift, residual.F if residual is not None else None, relu,
-                    l2norm, out, row_perm)
+                    l2norm, out, row_perm, tiled,
+                    wt_img=conv.tc_image() if tc_supported(in0.shape[1], in1.shape[1] if in1 is not None else 0,
+                                                            conv.out_channels, conv.kernel_size ** 3, l2norm) else None)
     return SparseTensor(out, coordinate_map_key=CoordinateMapKey(ts_out), coordinate_manager=mgr)
 
 

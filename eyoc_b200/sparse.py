@@ -38,6 +38,10 @@ class CoordinateMapKey:
         return f'CoordinateMapKey(tensor_stride={self.tensor_stride})'
 
 
+# L2 budget (bytes of input features) of one cloud group of the tile order (B200: 126 MB L2, shared with the outputs).
+TILE_GROUP_BYTES = 48e6
+
+
 class _Level:
     __slots__ = ('coords', 'n', 'keys', 'vals', 'cap', 'ts')
 
@@ -53,8 +57,10 @@ class CoordinateManager:
         self.device = coordinates.device
         self.levels = {}
         self._maps = {}
+        self._tiled = {}
         self._perms = {}
-        self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.max_batch = 0
+        self._status = torch.zeros(2, dtype=torch.int32, device=self.device)
         c = coordinates.to(torch.int32).contiguous()
         lv = _Level()
         lv.coords, lv.n, lv.ts = c, c.shape[0], 1
@@ -70,7 +76,7 @@ class CoordinateManager:
     # ------------------------------------------------------------------ levels
     def _check_status(self):
         if not self._checked:
-            st = int(self._status.item())
+            st, self.max_batch = (int(v) for v in self._status.tolist())
             if st & 1:
                 raise RuntimeError('coordinates outside the packed 16-bit range (batch 0..65535, xyz -32768..32767)')
             if st & 2:
@@ -126,6 +132,30 @@ class CoordinateManager:
                                                   _C.stream()))
             self._maps[key] = nbr
         return self._maps[key]
+
+    def tiled_map(self, ts_in, ts_out, ksize, transposed=False):
+        """(nbr_tiled [K, N_out], row_perm [N_out]) for the tensor-core convolution: output rows sorted by
+        (cloud group, neighbour-pattern bit mask) so that 128-row tiles are dense or skipped per kernel offset
+        (csrc/coordmap.cu: eyoc_tile_order).  The cloud group bounds the gather's L2 working set."""
+        key = (ts_in, ts_out, ksize, transposed)
+        if key not in self._tiled:
+            nbr = self.kernel_map(ts_in, ts_out, ksize, transposed)
+            self._check_status()
+            lin, lout = self.levels[ts_in], self.levels[ts_out]
+            K, n_out = nbr.shape
+            rows_per_cloud = max(1, lin.n // (self.max_batch + 1))
+            cin_hint = min(256, 64 * ts_in)          # widest input the maps of this level feed (ResUNet channel table)
+            group = max(1, min(self.max_batch + 1, int(TILE_GROUP_BYTES // (rows_per_cloud * 4 * cin_hint))))
+            perm = torch.empty(n_out, dtype=torch.int32, device=self.device)
+            tiled = torch.empty_like(nbr)
+            lib = _C.lib()
+            ws = torch.empty(max(lib.eyoc_tile_order_workspace_bytes(_C.c_int64(n_out)), 8), dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                _C.check(lib.eyoc_tile_order(_C.ptr(nbr), _C.c_int(K), _C.c_int64(n_out), _C.ptr(lout.coords), _C.c_int(group),
+                                             _C.c_int(self.max_batch), _C.ptr(perm), _C.ptr(tiled), _C.ptr(ws),
+                                             _C.c_size_t(ws.numel()), _C.stream()))
+            self._tiled[key] = (tiled, perm)
+        return self._tiled[key]
 
     def parity_perm(self, ts):
         """Row order of level ``ts`` grouped by parity class (CTA-uniform offsets for transposed convs)."""

@@ -94,7 +94,8 @@ int eyoc_kabsch_batched(const float* A, const float* B, float* w, int batch, int
  * (scripts/test_kitti.py:143-147) and under every ME.MinkowskiConvolution[Transpose] of
  * model/resunet.py:31-140.  coords are [n, 4] int32 (batch, x, y, z), 16-bit range per field.
  * Hash table: open addressing, capacity a power of two >= 2n; keys[capacity] u64, vals[capacity] i32.
- * status (device int32, caller-zeroed): bit 0 = coordinate out of range, bit 1 = duplicate coordinate. */
+ * status (device int32[2], caller-zeroed): status[0] bit 0 = coordinate out of range, bit 1 = duplicate coordinate;
+ * status[1] = largest batch index seen. */
 int eyoc_hash_build(const int32_t* coords, int64_t n, uint64_t* table_keys, int32_t* table_vals, int64_t capacity,
                     int32_t* status, eyoc_stream_t stream);
 /* Stride-2 coordinate set unique(floor(c / ts_out) * ts_out) in first-occurrence order (+ its hash table).
@@ -107,6 +108,13 @@ int eyoc_coords_downsample(const int32_t* coords, int64_t n, int ts_out, uint64_
  * step = +tensor_stride_in for a forward convolution, -tensor_stride_out for a transposed one. */
 int eyoc_kernel_map(const int32_t* out_coords, int64_t n_out, const uint64_t* in_table_keys, const int32_t* in_table_vals,
                     int64_t capacity, int ksize, int step, int32_t* nbr, eyoc_stream_t stream);
+/* Tile order for the tensor-core convolution: row_perm = output rows stably sorted by (cloud / group_clouds, bit mask
+ * of the kernel offsets that have a neighbour), nbr_tiled[k, i] = nbr[k, row_perm[i]].  Rows with the same neighbour
+ * pattern share 128-row tiles (dense or skipped (tile, offset) items) while each group of clouds stays contiguous
+ * (L2 working set of the gather).  K <= 27; max_batch = largest batch index (sizes the sort key). */
+size_t eyoc_tile_order_workspace_bytes(int64_t n_out);
+int eyoc_tile_order(const int32_t* nbr, int K, int64_t n_out, const int32_t* out_coords, int group_clouds, int max_batch,
+                    int32_t* row_perm, int32_t* nbr_tiled, void* workspace, size_t workspace_bytes, eyoc_stream_t stream);
 /* cls[i] = parity class (3 bits) of coords[i] / ts: groups the rows of a transposed stride-2 convolution by
  * their set of admissible kernel offsets. */
 int eyoc_parity_class(const int32_t* coords, int64_t n, int ts, int32_t* cls, eyoc_stream_t stream);
@@ -123,12 +131,15 @@ int eyoc_sparse_conv(const float* in0, int c0, const float* in1, int c1, const i
                      const float* residual, int relu, int l2norm, float* out, int cout, eyoc_stream_t stream);
 
 /* Tensor-core data path of the same operator (tcgen05.mma kind::tf32 with the 3-term hi/lo split, accumulators in
- * TMEM).  Weights must first be split and transposed once: weight [K, cin, cout] -> wt_hi, wt_lo [K, cout, cin].
- * Supported when eyoc_sparse_conv_tc_supported() returns 1 (cin, c0 multiples of 32; cout in {32,64,128,256}; K <= 32). */
-int eyoc_conv_split_weights(const float* weight, int K, int cin, int cout, float* wt_hi, float* wt_lo, eyoc_stream_t stream);
+ * TMEM).  Weights are first split and laid out once as shared-memory images (one TMA bulk copy per slab):
+ * weight [K, cin, cout] -> wt_img [K][cin/32][hi|lo][cout][32] (2 * K * cin * cout floats, 128B-swizzled rows).
+ * Supported when eyoc_sparse_conv_tc_supported() returns 1 (cin, c0 multiples of 32; cout in {32,64,128,256}; K <= 27).
+ * nbr_tiled != 0: nbr's columns are already in tile order (nbr_tiled[k, i] = nbr[k, row_perm[i]]), so the table is
+ * read coalesced; row_perm then only says where each tile row is written. */
+int eyoc_conv_split_weights(const float* weight, int K, int cin, int cout, float* wt_img, eyoc_stream_t stream);
 int eyoc_sparse_conv_tc_supported(int c0, int c1, int cout, int K, int l2norm);
 int eyoc_sparse_conv_tc(const float* in0, int c0, const float* in1, int c1, const int32_t* nbr, int K, int64_t n_out,
-                        const int32_t* row_perm, const float* wt_hi, const float* wt_lo, const float* scale,
+                        const int32_t* row_perm, int nbr_tiled, const float* wt_img, const float* scale,
                         const float* shift, const float* residual, int relu, int l2norm, float* out, int cout,
                         eyoc_stream_t stream);
 
