@@ -108,11 +108,12 @@ TILE_ORDER = True
 
 
 def split_weights(weight):
-    """[K, cin, cout] (or [cin, cout]) -> wt_img [K, cin/32, 2, cout, 32]: tf32 hi | lo parts laid out as the
-    swizzled shared-memory images the tensor-core kernel copies with one TMA bulk copy per slab."""
+    """[K, cin, cout] (or [cin, cout]) -> wt_img: per (k, 32-channel chunk, 128-channel part) the tf32 hi | lo rows laid
+    out as the swizzled shared-memory image the tensor-core kernel fetches with one TMA bulk copy."""
     w3 = weight if weight.dim() == 3 else weight[None]
     K, cin, cout = w3.shape
-    img = torch.empty((K, cin // 32, 2, cout, 32), dtype=torch.float32, device=weight.device)
+    n = _C.lib().eyoc_conv_weight_image_floats(_C.c_int(K), _C.c_int(cin), _C.c_int(cout))
+    img = torch.empty(n, dtype=torch.float32, device=weight.device)
     with torch.cuda.device(weight.device):
         _C.check(_C.lib().eyoc_conv_split_weights(_C.ptr(w3.contiguous()), _C.c_int(K), _C.c_int(cin), _C.c_int(cout),
                                                   _C.ptr(img), _C.stream()))

@@ -130,12 +130,21 @@ int eyoc_sparse_conv(const float* in0, int c0, const float* in1, int c1, const i
                      const int32_t* row_perm, const float* weight, const float* scale, const float* shift,
                      const float* residual, int relu, int l2norm, float* out, int cout, eyoc_stream_t stream);
 
-/* Tensor-core data path of the same operator (tcgen05.mma kind::tf32 with the 3-term hi/lo split, accumulators in
- * TMEM).  Weights are first split and laid out once as shared-memory images (one TMA bulk copy per slab):
- * weight [K, cin, cout] -> wt_img [K][cin/32][hi|lo][cout][32] (2 * K * cin * cout floats, 128B-swizzled rows).
- * Supported when eyoc_sparse_conv_tc_supported() returns 1 (cin, c0 multiples of 32; cout in {32,64,128,256}; K <= 27).
+/* Tensor-core data path of the same operator: tcgen05.mma kind::tf32, issued transposed (weights = M side, 256 gathered
+ * rows = N side), tf32 hi/lo split of both operands for fp32-level accuracy, accumulators in TMEM.
+ * Weights are first split and laid out once as shared-memory images (one TMA bulk copy per slab):
+ * weight [K, cin, cout] -> wt_img, eyoc_conv_weight_image_floats(K, cin, cout) floats.
+ * Supported when eyoc_sparse_conv_tc_supported() returns 1 (cin, c0 multiples of 32; cout in {32,64,128,256}; K <= 27;
+ * l2norm only for cout <= 128).
  * nbr_tiled != 0: nbr's columns are already in tile order (nbr_tiled[k, i] = nbr[k, row_perm[i]]), so the table is
  * read coalesced; row_perm then only says where each tile row is written. */
+size_t eyoc_conv_weight_image_floats(int K, int cin, int cout);
+/* Measurement aid (tools/conv_ablate.py): switch off parts of the tensor-core kernel (bit 0 MMAs, bit 1 gather +
+ * x_lo pass, bit 2 weight-slab copies) to time the others alone.  0 = normal operation; results are invalid otherwise. */
+int eyoc_debug_conv_ablate(int flags);
+/* bit 3 of the flags: the first 1024 CTAs record clock64 at {start, work list built, main loop done, accumulators
+ * complete, epilogue done} and their item count; this copies the [1024][6] table to the host. */
+int eyoc_debug_conv_times(long long* host_out_1024x6);
 int eyoc_conv_split_weights(const float* weight, int K, int cin, int cout, float* wt_img, eyoc_stream_t stream);
 int eyoc_sparse_conv_tc_supported(int c0, int c1, int cout, int K, int l2norm);
 int eyoc_sparse_conv_tc(const float* in0, int c0, const float* in1, int c1, const int32_t* nbr, int K, int64_t n_out,
