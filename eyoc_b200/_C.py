@@ -32,7 +32,8 @@ class SC2Layout(ctypes.Structure):
     """struct eyoc_sc2_layout."""
     _fields_ = [(k, c_size_t) for k in ('points', 'hard_bits', 'tight_bits', 'vbuf', 'u', 'confidence', 'scores', 'seeds',
                                         'topk1', 'topk2', 'local_v', 'seed_weights', 'seed_trans', 'counters',
-                                        'global_iters', 'local_notclose', 'best_seed', 'refine_counts', 'total')] + \
+                                        'global_iters', 'local_notclose', 'best_seed', 'refine_counts', 'total',
+                                        'csr_rowptr', 'csr_cols', 'csr_vals', 'csr_capacity')] + \
                [(k, c_int) for k in ('words_per_row', 'k1', 'k2', 'num_seeds')]
 
 

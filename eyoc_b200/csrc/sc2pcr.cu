@@ -89,9 +89,108 @@ first_order_bits_kernel(const Pt* __restrict__ P, int n, int W, float d_thre, fl
 }
 
 // ------------------------------------------------------------------- leading eigenvector (power iteration)
-// SC2_PCR.py:179-190.  One launch per iteration; warp per row walks the set bits of hard[i] and recomputes
-// SC_ij = clamp(1 - cross^2 / d^2, 0) (SC2_PCR.py:341).  The last CTA of each pair normalises, applies the
-// torch.allclose stopping rule and publishes the iteration count; later launches exit at once when done.
+// SC2_PCR.py:179-190.  The soft SC matrix  SC_ij = clamp(1 - cross^2 / d^2, 0)  (SC2_PCR.py:341) is non-zero exactly
+// where `hard` is set and does not change over the <= 20 iterations, so it is evaluated ONCE into a CSR image
+// (uint16 column + fp32 value per set bit, rows in bit order) and every iteration is a sparse mat-vec over it.
+// Pairs whose hard matrix is denser than the caller-sized CSR capacity keep the recompute-from-coordinates path.
+struct Csr {
+    uint32_t* rowptr;    // [batch, n + 1]
+    uint16_t* cols;      // [batch, cap]
+    float* vals;         // [batch, cap]
+    int* ok;             // [batch] 1 = CSR image valid
+    size_t cap;
+};
+
+// grid (ceil(n / 8), batch): warp per row -> number of set bits
+__global__ void __launch_bounds__(256)
+csr_count_kernel(const uint32_t* __restrict__ hard, int n, int W, uint32_t* __restrict__ rowptr) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const uint32_t* row = hard + ((size_t)b * n + i) * W;
+    int c = 0;
+    for (int w = lane; w < W; w += 32) c += __popc(row[w]);
+    c = warp_sum_i(c);
+    if (lane == 0) rowptr[(size_t)b * (n + 1) + i + 1] = (uint32_t)c;
+}
+
+// grid (batch): in-place inclusive scan of rowptr[1..n] (rowptr[0] = 0); ok = total fits the capacity
+__global__ void __launch_bounds__(1024)
+csr_scan_kernel(uint32_t* __restrict__ rowptr, int n, size_t cap, int* __restrict__ ok) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry_s;
+    uint32_t* r = rowptr + (size_t)blockIdx.x * (n + 1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { carry_s = 0; r[0] = 0; }
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        uint32_t x = i < n ? r[i + 1] : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t s = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += y;
+            }
+            wsum[lane] = s;
+        }
+        __syncthreads();
+        const uint32_t carry = carry_s;
+        const uint32_t incl = x + (warp ? wsum[warp - 1] : 0u) + carry;
+        if (i < n) r[i + 1] = incl;
+        __syncthreads();
+        if (tid == 1023) carry_s = incl;
+        __syncthreads();
+    }
+    if (tid == 0) ok[blockIdx.x] = (size_t)r[n] <= cap ? 1 : 0;
+}
+
+// grid (ceil(n / 8), batch): warp per row writes (column, SC value) for every set bit, in bit order
+__global__ void __launch_bounds__(256)
+csr_fill_kernel(const Pt* __restrict__ P, const uint32_t* __restrict__ hard, int n, int W, float d_sq, Csr csr) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n || !csr.ok[b]) return;
+    P += (size_t)b * n;
+    const uint32_t* row = hard + ((size_t)b * n + i) * W;
+    uint16_t* cols = csr.cols + (size_t)b * csr.cap;
+    float* vals = csr.vals + (size_t)b * csr.cap;
+    uint32_t base = csr.rowptr[(size_t)b * (n + 1) + i];
+    const Pt me = load_pt(P + i);
+    for (int w0 = 0; w0 < W; w0 += 32) {
+        const int w = w0 + lane;
+        uint32_t m = w < W ? row[w] : 0u;
+        const int c = __popc(m);
+        int x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        uint32_t pos = base + (uint32_t)(x - c);
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            const int j = w * 32 + bit;
+            const float cd = cross_dist(me, load_pt(P + j));
+            cols[pos] = (uint16_t)j;
+            vals[pos] = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fmul_rn(cd, cd), d_sq)), 0.f);
+            ++pos;
+        }
+        base += (uint32_t)__shfl_sync(0xffffffffu, x, 31);
+    }
+}
+
+// One launch per iteration; warp per row.  The last CTA of each pair normalises, applies the torch.allclose
+// stopping rule and publishes the iteration count; later launches exit at once when done.
 struct PowerState {
     int* done;          // [batch]
     int* iters;         // [batch]
@@ -101,7 +200,7 @@ struct PowerState {
 __global__ void __launch_bounds__(256)
 power_step_kernel(const Pt* __restrict__ P, const uint32_t* __restrict__ hard, int n, int W, float d_sq, int t,
                   int num_iterations, float* __restrict__ vbuf, float* __restrict__ u, float* __restrict__ conf,
-                  PowerState st) {
+                  PowerState st, Csr csr) {
     const int b = blockIdx.y;
     if (st.done[b]) return;
     P += (size_t)b * n;
@@ -113,21 +212,40 @@ power_step_kernel(const Pt* __restrict__ P, const uint32_t* __restrict__ hard, i
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.x * 8 + warp;
     if (i < n) {
-        const Pt me = load_pt(P + i);
         float acc = 0.f;
-        for (int w = lane; w < W; w += 32) {
-            uint32_t m = hard[(size_t)i * W + w];
-            while (m) {
-                const int bit = __ffs(m) - 1;
-                m &= m - 1;
-                const int j = w * 32 + bit;
-                const float c = cross_dist(me, load_pt(P + j));
-                const float sc = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fmul_rn(c, c), d_sq)), 0.f);
-                const float vj = (t == 1) ? 1.0f : __ldg(vprev + j);
-                acc = __fmaf_rn(sc, vj, acc);
+        if (csr.ok[b]) {
+            const uint16_t* cols = csr.cols + (size_t)b * csr.cap;
+            const float* vals = csr.vals + (size_t)b * csr.cap;
+            const uint32_t s = csr.rowptr[(size_t)b * (n + 1) + i], e = csr.rowptr[(size_t)b * (n + 1) + i + 1];
+            if (t == 1) {
+                for (uint32_t p = s + lane; p < e; p += 32) acc = __fmaf_rn(__ldg(vals + p), 1.0f, acc);
+            } else {
+                uint32_t p = s + lane;
+                for (; p + 96 < e; p += 128) {               // 4 independent gathers in flight per lane
+                    const float a0 = __ldg(vals + p), a1 = __ldg(vals + p + 32), a2 = __ldg(vals + p + 64), a3 = __ldg(vals + p + 96);
+                    const float v0 = __ldg(vprev + __ldg(cols + p)), v1 = __ldg(vprev + __ldg(cols + p + 32));
+                    const float v2 = __ldg(vprev + __ldg(cols + p + 64)), v3 = __ldg(vprev + __ldg(cols + p + 96));
+                    acc = __fmaf_rn(a0, v0, acc); acc = __fmaf_rn(a1, v1, acc);
+                    acc = __fmaf_rn(a2, v2, acc); acc = __fmaf_rn(a3, v3, acc);
+                }
+                for (; p < e; p += 32) acc = __fmaf_rn(__ldg(vals + p), __ldg(vprev + __ldg(cols + p)), acc);
+            }
+        } else {
+            const Pt me = load_pt(P + i);
+            for (int w = lane; w < W; w += 32) {
+                uint32_t m = hard[(size_t)i * W + w];
+                while (m) {
+                    const int bit = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int j = w * 32 + bit;
+                    const float c = cross_dist(me, load_pt(P + j));
+                    const float sc = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fmul_rn(c, c), d_sq)), 0.f);
+                    const float vj = (t == 1) ? 1.0f : __ldg(vprev + j);
+                    acc = __fmaf_rn(sc, vj, acc);
+                }
             }
         }
-        acc = warp_sum(acc);
+    acc = warp_sum(acc);
         if (lane == 0) u[i] = acc;
     }
     // ---- last CTA of this pair: normalise + allclose
@@ -762,8 +880,14 @@ extern "C" int eyoc_sc2pcr_layout(int batch, int n, int num_seeds, const eyoc_sc
     L->local_v = c.off; c.take<float>(B * S * I * MAXK);
     L->seed_weights = c.off; c.take<float>(B * S * MAXK);
     L->seed_trans = c.off; c.take<float>(B * S * 16);
+    // CSR image of the soft SC matrix: capacity = 1/8 of the dense matrix (denser pairs recompute from coordinates)
+    const size_t cap = N * N / 8 > 64 * N ? N * N / 8 : (N * N < 64 * N ? N * N : 64 * N);
+    L->csr_capacity = cap;
+    L->csr_rowptr = c.off; c.take<uint32_t>(B * (N + 1));
+    L->csr_cols = c.off; c.take<uint16_t>(B * cap);
+    L->csr_vals = c.off; c.take<float>(B * cap);
     // ---- small zero-initialised control block (one memset)
-    L->counters = c.off; c.take<unsigned int>(B * (I + 1) + 2 * B);   // tickets | done | (pad)
+    L->counters = c.off; c.take<unsigned int>(B * (I + 1) + 3 * B);   // tickets | done | csr_ok
     L->global_iters = c.off; c.take<int>(B);
     L->local_notclose = c.off; c.take<int>(B * (I + 1) + B);          // notclose | local_iters
     L->best_seed = c.off; c.take<int>(B);
@@ -821,6 +945,8 @@ extern "C" int eyoc_sc2pcr(const float* src, const float* tgt, int batch, int n,
     float* seed_trans = (float*)(ws + L.seed_trans);
     unsigned int* tickets = (unsigned int*)(ws + L.counters);
     int* done = (int*)(tickets + (size_t)batch * (I + 1));
+    int* csr_ok = done + batch;
+    Csr csr{(uint32_t*)(ws + L.csr_rowptr), (uint16_t*)(ws + L.csr_cols), (float*)(ws + L.csr_vals), csr_ok, L.csr_capacity};
     int* global_iters = (int*)(ws + L.global_iters);
     int* local_notclose = (int*)(ws + L.local_notclose);
     int* local_iters = local_notclose + (size_t)batch * (I + 1);
@@ -841,8 +967,14 @@ extern "C" int eyoc_sc2pcr(const float* src, const float* tgt, int batch, int n,
             conf_use = hooks->confidence;
         } else if (!(hooks && hooks->seeds)) {
             PowerState st{done, global_iters, tickets};
+            csr_count_kernel<<<dim3((n + 7) / 8, batch), 256, 0, stream>>>(hard, n, W, csr.rowptr);
+            EYOC_LAUNCH_CHECK();
+            csr_scan_kernel<<<batch, 1024, 0, stream>>>(csr.rowptr, n, csr.cap, csr.ok);
+            EYOC_LAUNCH_CHECK();
+            csr_fill_kernel<<<dim3((n + 7) / 8, batch), 256, 0, stream>>>(P, hard, n, W, cfg->d_thre_sq, csr);
+            EYOC_LAUNCH_CHECK();
             for (int t = 1; t <= I; ++t) {
-                power_step_kernel<<<dim3((n + 7) / 8, batch), 256, 0, stream>>>(P, hard, n, W, cfg->d_thre_sq, t, I, vbuf, u, conf, st);
+                power_step_kernel<<<dim3((n + 7) / 8, batch), 256, 0, stream>>>(P, hard, n, W, cfg->d_thre_sq, t, I, vbuf, u, conf, st, csr);
                 EYOC_LAUNCH_CHECK();
             }
         }

@@ -72,7 +72,8 @@ typedef struct {
 /* Byte offsets of the intermediate buffers inside the workspace (for tests and diagnostics). */
 typedef struct {
     size_t points, hard_bits, tight_bits, vbuf, u, confidence, scores, seeds, topk1, topk2, local_v,
-        seed_weights, seed_trans, counters, global_iters, local_notclose, best_seed, refine_counts, total;
+        seed_weights, seed_trans, counters, global_iters, local_notclose, best_seed, refine_counts, total,
+        csr_rowptr, csr_cols, csr_vals, csr_capacity;
     int words_per_row, k1, k2, num_seeds;
 } eyoc_sc2_layout;
 
