@@ -66,11 +66,8 @@ __global__ void hash_build_kernel(const int* __restrict__ coords, int n, unsigne
     const int4 c = reinterpret_cast<const int4*>(coords)[i];
     if (!(c.x >= 0 && c.x <= 65535 && in_range16(c.y) && in_range16(c.z) && in_range16(c.w))) { atomicOr(status, 1); return; }
     hash_insert_min(keys, vals, cap, pack4(c.x, c.y, c.z, c.w), i);
-    // status[1] = largest batch index (one atomic per warp)
-    int b = c.x;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) b = max(b, __shfl_xor_sync(__activemask(), b, o));
-    if ((threadIdx.x & 31) == 0 || i == 0) atomicMax(status + 1, b);
+    // status[1] = largest batch index: atomics only when the running maximum actually moves
+    if (c.x > *((volatile int*)(status + 1))) atomicMax(status + 1, c.x);
 }
 
 __global__ void hash_check_unique_kernel(const int* __restrict__ coords, int n, const unsigned long long* keys, const int* vals,
@@ -199,6 +196,38 @@ __global__ void kernel_map_kernel(const int* __restrict__ out_coords, int n_out,
     int v = -1;
     if (in_range16(x) && in_range16(y) && in_range16(z)) v = hash_lookup(keys, vals, cap, pack4(c.x, x, y, z));
     nbr[(size_t)k * n_out + o] = v;
+}
+
+// Stride-1 map of a coordinate set onto itself: offsets come in mirrored pairs (k, K^3-1-k) and i = nbr[k, o] <=>
+// o = nbr[K^3-1-k, i], so only the first half of the offsets is probed; every hit is written twice (the table is
+// pre-filled with -1 and the centre offset is the identity).
+__global__ void kernel_map_sym_kernel(const int* __restrict__ coords, int n, const unsigned long long* __restrict__ keys,
+                                      const int* __restrict__ vals, long long cap, int ksize, int step, int* __restrict__ nbr) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;                       // 0 .. K^3/2 (the last one is the centre)
+    if (o >= n) return;
+    const int K3 = ksize * ksize * ksize;
+    if (k == K3 / 2) { nbr[(size_t)k * n + o] = o; return; }
+    const int r = (ksize - 1) / 2;
+    const int ix = k % ksize - r, iy = (k / ksize) % ksize - r, iz = k / (ksize * ksize) - r;
+    const int4 c = reinterpret_cast<const int4*>(coords)[o];
+    const int x = c.y + ix * step, y = c.z + iy * step, z = c.w + iz * step;
+    if (!(in_range16(x) && in_range16(y) && in_range16(z))) return;
+    const int v = hash_lookup(keys, vals, cap, pack4(c.x, x, y, z));
+    if (v >= 0) {
+        nbr[(size_t)k * n + o] = v;
+        nbr[(size_t)(K3 - 1 - k) * n + v] = o;
+    }
+}
+
+// Transposed (fine <- coarse) map from the forward strided map between the same two levels:
+// f = down[k, c]  <=>  c = up[k, f]  (same k, MinkowskiEngine's no-flip convention).
+__global__ void kernel_map_transpose_kernel(const int* __restrict__ down, int n_coarse, int n_fine, int* __restrict__ up) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t k = blockIdx.y;
+    if (c >= n_coarse) return;
+    const int f = __ldg(down + k * n_coarse + c);
+    if (f >= 0) up[k * n_fine + f] = c;
 }
 
 // rows of one map grouped by the parity class of (x, y, z) / ts  (8 classes): perm sorted by class,
@@ -333,6 +362,33 @@ extern "C" int eyoc_kernel_map(const int32_t* out_coords, int64_t n_out, const u
     dim3 grid((unsigned)((n_out + 255) / 256), ksize * ksize * ksize);
     kernel_map_kernel<<<grid, 256, 0, stream>>>(out_coords, (int)n_out, (const unsigned long long*)in_table_keys, in_table_vals, capacity,
                                                 ksize, step, nbr);
+    EYOC_LAUNCH_CHECK();
+    return EYOC_OK;
+}
+
+extern "C" int eyoc_kernel_map_self(const int32_t* coords, int64_t n, const uint64_t* table_keys, const int32_t* table_vals,
+                                    int64_t capacity, int ksize, int step, int32_t* nbr, cudaStream_t stream) {
+    EYOC_CHECK_ARG(coords && table_keys && table_vals && nbr, "eyoc_kernel_map_self: null argument");
+    EYOC_CHECK_ARG(ksize >= 1 && (ksize & 1) && ksize <= 7, "eyoc_kernel_map_self: kernel size must be odd and <= 7 (got %d)", ksize);
+    EYOC_CHECK_ARG(n >= 0 && n < (1ll << 31), "eyoc_kernel_map_self: bad n");
+    if (n == 0) return EYOC_OK;
+    const int K3 = ksize * ksize * ksize;
+    EYOC_CUDA(cudaMemsetAsync(nbr, 0xff, (size_t)K3 * n * sizeof(int32_t), stream));
+    dim3 grid((unsigned)((n + 255) / 256), K3 / 2 + 1);
+    kernel_map_sym_kernel<<<grid, 256, 0, stream>>>(coords, (int)n, (const unsigned long long*)table_keys, table_vals, capacity, ksize,
+                                                    step, nbr);
+    EYOC_LAUNCH_CHECK();
+    return EYOC_OK;
+}
+
+extern "C" int eyoc_kernel_map_transpose(const int32_t* nbr_down, int64_t n_coarse, int64_t n_fine, int K, int32_t* nbr_up,
+                                         cudaStream_t stream) {
+    EYOC_CHECK_ARG(nbr_down && nbr_up && K >= 1, "eyoc_kernel_map_transpose: bad argument");
+    EYOC_CHECK_ARG(n_coarse >= 0 && n_fine >= 0 && n_coarse < (1ll << 31) && n_fine < (1ll << 31), "eyoc_kernel_map_transpose: bad sizes");
+    if (n_fine == 0) return EYOC_OK;
+    EYOC_CUDA(cudaMemsetAsync(nbr_up, 0xff, (size_t)K * n_fine * sizeof(int32_t), stream));
+    if (n_coarse == 0) return EYOC_OK;
+    kernel_map_transpose_kernel<<<dim3((unsigned)((n_coarse + 255) / 256), K), 256, 0, stream>>>(nbr_down, (int)n_coarse, (int)n_fine, nbr_up);
     EYOC_LAUNCH_CHECK();
     return EYOC_OK;
 }

@@ -28,6 +28,13 @@ __device__ __forceinline__ unsigned long long pack_key(float v, int j) {
     return ((unsigned long long)enc << 32) | (unsigned int)j;
 }
 
+// distance value the reference compares, from the raw accumulator
+template <int FORM>
+__device__ __forceinline__ float value_of(float a) {
+    if (FORM == 1) return __fsqrt_rn(__fadd_rn(__fsub_rn(2.f, __fmul_rn(2.f, a)), 1e-6f));
+    return a;
+}
+
 template <int FORM>
 __global__ void __launch_bounds__(NTHREADS, 2)
 knn1_kernel(const float* __restrict__ Q, const float* __restrict__ R, int nq, int nr, int dim, int dimp,
@@ -63,10 +70,10 @@ knn1_kernel(const float* __restrict__ Q, const float* __restrict__ R, int nq, in
         }
     }
 
-    float bestv[8];
+    float best[8];     // winner's raw accumulator (its distance value is value_of(best))
     int bestj[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { bestv[i] = __int_as_float(0x7f800000); bestj[i] = -1; }
+    for (int i = 0; i < 8; ++i) { best[i] = (FORM == 1) ? __int_as_float(0xff800000) : __int_as_float(0x7f800000); bestj[i] = -1; }
     int firstj = -1;
 
     const int tile0 = blockIdx.y * tiles_per_split;
@@ -121,7 +128,10 @@ knn1_kernel(const float* __restrict__ Q, const float* __restrict__ R, int nq, in
                     }
             }
         }
-        // running argmin; this thread visits its columns in ascending j, so strict '<' keeps the first
+        // running argmin; this thread visits its columns in ascending j, so strict '<' keeps the first.
+        // Fast reject on the raw accumulator: form 1's  sqrt((2 - 2 acc) + 1e-6)  is monotonically non-increasing in
+        // acc (every rounding step is monotonic), so a candidate can only win when acc > the winner's acc; the exact
+        // rounded value is formed and compared only then (a handful of times per row).  NaN always takes the slow path.
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int col = r0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
@@ -129,10 +139,16 @@ knn1_kernel(const float* __restrict__ Q, const float* __restrict__ R, int nq, in
                 if (firstj < 0) firstj = col;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    float v = acc[i][j];
-                    if (FORM == 1) v = __fsqrt_rn(__fadd_rn(__fsub_rn(2.f, __fmul_rn(2.f, v)), 1e-6f));
-                    const bool take = (v < bestv[i]) || (v != v && bestv[i] == bestv[i]);
-                    if (take) { bestv[i] = v; bestj[i] = col; }
+                    const float a = acc[i][j];
+                    const bool maybe = (FORM == 1) ? !(a <= best[i]) : !(a >= best[i]);
+                    if (maybe) {
+                        const float v = value_of<FORM>(a), bv = value_of<FORM>(best[i]);
+                        const bool take = (v < bv) || (v != v && bv == bv);
+                        if (take) {
+                            bestj[i] = col;
+                            best[i] = (FORM == 1 && v != v) ? __int_as_float(0x7f800000) : a;    // +inf accumulator <-> NaN value
+                        }
+                    }
                 }
             }
         }
@@ -141,7 +157,7 @@ knn1_kernel(const float* __restrict__ Q, const float* __restrict__ R, int nq, in
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         unsigned long long key = 0xffffffffffffffffull;
-        if (bestj[i] >= 0) key = pack_key(bestv[i], bestj[i]);
+        if (bestj[i] >= 0) key = pack_key(value_of<FORM>(best[i]), bestj[i]);
         else if (firstj >= 0) key = pack_key(__int_as_float(0x7f800000), firstj);   // all +inf
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) {

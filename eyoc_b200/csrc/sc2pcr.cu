@@ -52,6 +52,8 @@ __device__ __forceinline__ float cross_dist(const Pt& a, const Pt& b) {
 
 // ------------------------------------------------------------------------------- first-order bit rows
 // grid (ceil(n/32), batch); lane = row, the 8 warps split the 32-bit words of each 1024-column tile.
+// cross_dist(i, j) == cross_dist(j, i) bit for bit ((a-b)^2 == (b-a)^2), so only the 32x32 bit blocks on and above the
+// diagonal are evaluated; the mirrored block is the bit transpose, assembled with one warp ballot per column.
 __global__ void __launch_bounds__(256)
 first_order_bits_kernel(const Pt* __restrict__ P, int n, int W, float d_thre, float d_half,
                         uint32_t* __restrict__ hard, uint32_t* __restrict__ tight) {
@@ -61,30 +63,40 @@ first_order_bits_kernel(const Pt* __restrict__ P, int n, int W, float d_thre, fl
     hard += (size_t)b * n * W;
     tight += (size_t)b * n * W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i = blockIdx.x * 32 + lane;
+    const int I = blockIdx.x;                        // 32-row block == word index of these rows
+    const int i = I * 32 + lane;
+    const bool row_ok = i < n;
     Pt me = load_pt(P + min(i, n - 1));
-    for (int c0 = 0; c0 < n; c0 += CT) {
+    for (int c0 = (I * 32 / CT) * CT; c0 < n; c0 += CT) {
         __syncthreads();
         for (int t = threadIdx.x; t < CT; t += 256) tile[t] = load_pt(P + min(c0 + t, n - 1));
         __syncthreads();
-        const int words = min(CT, n - c0 + 31) / 32;
         for (int wl = warp; wl < (CT / 32); wl += 8) {
-            if (c0 + wl * 32 >= n) break;
-            uint32_t hb = 0, tb = 0;
+            const int J = (c0 >> 5) + wl;            // word (32-column block) index
+            if (J * 32 >= n) break;
+            if (J < I) continue;                      // below the diagonal: written by the mirrored block
+            uint32_t hb = 0, tb = 0, mh = 0, mt = 0;
 #pragma unroll 4
             for (int bit = 0; bit < 32; ++bit) {
-                const int j = c0 + wl * 32 + bit;
+                const int j = J * 32 + bit;
                 const float c = cross_dist(me, tile[wl * 32 + bit]);
-                const bool ok = j < n;
-                hb |= (uint32_t)(ok && c < d_thre) << bit;
-                tb |= (uint32_t)(ok && c < d_half) << bit;
+                const bool ok = row_ok && j < n;
+                const bool h = ok && c < d_thre, t = ok && c < d_half;
+                hb |= (uint32_t)h << bit;
+                tb |= (uint32_t)t << bit;
+                const uint32_t bh = __ballot_sync(0xffffffffu, h), bt = __ballot_sync(0xffffffffu, t);
+                if (lane == bit) { mh = bh; mt = bt; }    // row J*32+bit, columns I*32 .. I*32+31
             }
-            if (i < n) {
-                hard[(size_t)i * W + (c0 >> 5) + wl] = hb;
-                tight[(size_t)i * W + (c0 >> 5) + wl] = tb;
+            if (row_ok) {
+                hard[(size_t)i * W + J] = hb;
+                tight[(size_t)i * W + J] = tb;
+            }
+            const int jrow = J * 32 + lane;
+            if (J != I && jrow < n) {
+                hard[(size_t)jrow * W + I] = mh;
+                tight[(size_t)jrow * W + I] = mt;
             }
         }
-        (void)words;
     }
 }
 

@@ -126,10 +126,21 @@ class CoordinateManager:
             step = -ts_out if transposed else ts_in
             K = ksize ** 3
             nbr = torch.empty((K, lout.n), dtype=torch.int32, device=self.device)
+            lib = _C.lib()
             with torch.cuda.device(self.device):
-                _C.check(_C.lib().eyoc_kernel_map(_C.ptr(lout.coords), _C.c_int64(lout.n), _C.ptr(lin.keys), _C.ptr(lin.vals),
-                                                  _C.c_int64(lin.cap), _C.c_int(ksize), _C.c_int(step), _C.ptr(nbr),
-                                                  _C.stream()))
+                if transposed and ts_in == 2 * ts_out:
+                    # mirror of the forward strided map (built once by the encoder, or here)
+                    down = self.kernel_map(ts_out, ts_in, ksize, False)
+                    _C.check(lib.eyoc_kernel_map_transpose(_C.ptr(down), _C.c_int64(lin.n), _C.c_int64(lout.n), _C.c_int(K),
+                                                           _C.ptr(nbr), _C.stream()))
+                elif not transposed and ts_in == ts_out:
+                    _C.check(lib.eyoc_kernel_map_self(_C.ptr(lout.coords), _C.c_int64(lout.n), _C.ptr(lin.keys), _C.ptr(lin.vals),
+                                                      _C.c_int64(lin.cap), _C.c_int(ksize), _C.c_int(step), _C.ptr(nbr),
+                                                      _C.stream()))
+                else:
+                    _C.check(lib.eyoc_kernel_map(_C.ptr(lout.coords), _C.c_int64(lout.n), _C.ptr(lin.keys), _C.ptr(lin.vals),
+                                                 _C.c_int64(lin.cap), _C.c_int(ksize), _C.c_int(step), _C.ptr(nbr),
+                                                 _C.stream()))
             self._maps[key] = nbr
         return self._maps[key]
 

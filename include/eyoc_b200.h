@@ -109,6 +109,14 @@ int eyoc_coords_downsample(const int32_t* coords, int64_t n, int ts_out, uint64_
  * step = +tensor_stride_in for a forward convolution, -tensor_stride_out for a transposed one. */
 int eyoc_kernel_map(const int32_t* out_coords, int64_t n_out, const uint64_t* in_table_keys, const int32_t* in_table_vals,
                     int64_t capacity, int ksize, int step, int32_t* nbr, eyoc_stream_t stream);
+/* The same table for a stride-1 map of a coordinate set onto itself (coords = the set that built the table, step = its
+ * tensor stride): mirrored offsets are filled from one probe (i = nbr[k, o] <=> o = nbr[K^3-1-k, i]). */
+int eyoc_kernel_map_self(const int32_t* coords, int64_t n, const uint64_t* table_keys, const int32_t* table_vals,
+                         int64_t capacity, int ksize, int step, int32_t* nbr, eyoc_stream_t stream);
+/* Transposed-convolution table from the forward strided one between the same levels:
+ * nbr_up[k, f] = c  <=>  nbr_down[k, c] = f  (nbr_down [K, n_coarse] -> nbr_up [K, n_fine], -1 elsewhere). */
+int eyoc_kernel_map_transpose(const int32_t* nbr_down, int64_t n_coarse, int64_t n_fine, int K, int32_t* nbr_up,
+                              eyoc_stream_t stream);
 /* Tile order for the tensor-core convolution: row_perm = output rows stably sorted by (cloud / group_clouds, bit mask
  * of the kernel offsets that have a neighbour), nbr_tiled[k, i] = nbr[k, row_perm[i]].  Rows with the same neighbour
  * pattern share 128-row tiles (dense or skipped (tile, offset) items) while each group of clouds stays contiguous
