@@ -297,7 +297,7 @@ def run_ours(args):
                   f'ms/launch={d[1] / d[0]:8.3f} algGB/s={d[2] / d[1] / 1e6:8.1f} TFLOP/s={d[3] / d[1] / 1e9:7.2f}', file=sys.stderr)
     peak, peak_src = _peaks()
     achieved = tot_bytes / (tot_ms / 1e3) / 1e9 if tot_ms > 0 else 0.0
-    roofline = {'bound': 'hbm', 'kernel': 'sparse_conv_tiled_kernel (all tiled conv launches of the timed region)',
+    roofline = {'bound': 'hbm', 'kernel': 'sparse_conv_tc_kernel (all tensor-core sparse-conv launches of the timed region)',
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
                 'peak_source': peak_src, 'launches_timed': n_tiled, 'avg_launch_ms': tot_ms / max(n_tiled, 1),
                 'share_of_step': tot_ms / ms if ms > 0 else None,
