@@ -222,7 +222,7 @@ def run_ours(args):
         rec = pipe.records(out, list(range(rank * P, rank * P + P)))
         return gather_records(rec, P * world), out
 
-    prefetch = PlanPrefetcher(pipe, (sizes for _ in range(K + 2)))         # host RNG planning of block i+1 overlaps block i
+    prefetch = None
 
     def step_e2e():
         c = coords_h.to(dev, non_blocking=True)
@@ -245,13 +245,19 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_ev = []
     ev0.record()
+    step_ev = [ev0]
     for _ in range(K):
         allrec, out = step_resident()
+        step_ev.append(torch.cuda.Event(enable_timing=True))
+        step_ev[-1].record()
     ev1.record()
     barrier()
     launches = int(lib.eyoc_launch_count() - launches0)
     prof, enn.PROFILE = enn.PROFILE, None
     ms = ev0.elapsed_time(ev1)
+    if args.conv_breakdown or world > 1:
+        print(f'[rank {rank}] per-step ms: ' + ' '.join(f'{a.elapsed_time(b):.1f}' for a, b in zip(step_ev[:-1], step_ev[1:])),
+              file=sys.stderr, flush=True)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -259,6 +265,7 @@ def run_ours(args):
     value = P * world * K / (ms / 1e3)
 
     # ---- end-to-end timing through the public API with host inputs
+    prefetch = PlanPrefetcher(pipe, (sizes for _ in range(K + 2)))         # host RNG planning of block i+1 overlaps block i
     for _ in range(2):
         step_e2e()
     barrier()

@@ -8,7 +8,7 @@ import sys
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ['capi.cu', 'knn.cu', 'sc2pcr.cu', 'coordmap.cu', 'sparse_conv.cu', 'sparse_conv_tc.cu']
+SOURCES = ['capi.cu', 'knn.cu', 'sc2pcr.cu', 'coordmap.cu', 'sparse_conv.cu', 'sparse_conv_tc.cu', 'host_plan.cu']
 LIB = os.path.join(os.path.dirname(HERE), 'libeyoc_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
@@ -50,7 +50,7 @@ def build(force=False, verbose=False):
         list(ex.map(compile_one, jobs))
     objs = [os.path.join(objdir, s.replace('.cu', '.o')) for s in srcs]
     if force or jobs or _stale(LIB, objs):
-        r = subprocess.run([NVCC, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', LIB, *objs, '-lcudart'],
+        r = subprocess.run([NVCC, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', LIB, *objs, '-lcudart', '-Xcompiler', '-pthread'],
                            capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')

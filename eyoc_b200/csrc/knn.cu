@@ -132,21 +132,34 @@ knn1_kernel(const float* __restrict__ Q, const float* __restrict__ R, int nq, in
         // Fast reject on the raw accumulator: form 1's  sqrt((2 - 2 acc) + 1e-6)  is monotonically non-increasing in
         // acc (every rounding step is monotonic), so a candidate can only win when acc > the winner's acc; the exact
         // rounded value is formed and compared only then (a handful of times per row).  NaN always takes the slow path.
+        bool any = false;            // does any of the 64 accumulators beat its row's current winner?  (columns past
+#pragma unroll                       //  nr hold zero rows: a false alarm at worst, re-checked below)
+        for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int col = r0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
-            if (col < nr) {
-                if (firstj < 0) firstj = col;
+            for (int i = 0; i < 8; ++i) any |= (FORM == 1) ? !(acc[i][j] <= best[i]) : !(acc[i][j] >= best[i]);
+        if (firstj < 0) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float a = acc[i][j];
-                    const bool maybe = (FORM == 1) ? !(a <= best[i]) : !(a >= best[i]);
-                    if (maybe) {
-                        const float v = value_of<FORM>(a), bv = value_of<FORM>(best[i]);
-                        const bool take = (v < bv) || (v != v && bv == bv);
-                        if (take) {
-                            bestj[i] = col;
-                            best[i] = (FORM == 1 && v != v) ? __int_as_float(0x7f800000) : a;    // +inf accumulator <-> NaN value
+            for (int j = 7; j >= 0; --j) {
+                const int col = r0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+                if (col < nr) firstj = col;
+            }
+        }
+        if (any) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int col = r0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+                if (col < nr) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float a = acc[i][j];
+                        const bool maybe = (FORM == 1) ? !(a <= best[i]) : !(a >= best[i]);
+                        if (maybe) {
+                            const float v = value_of<FORM>(a), bv = value_of<FORM>(best[i]);
+                            const bool take = (v < bv) || (v != v && bv == bv);
+                            if (take) {
+                                bestj[i] = col;
+                                best[i] = (FORM == 1 && v != v) ? __int_as_float(0x7f800000) : a;    // +inf accumulator <-> NaN value
+                            }
                         }
                     }
                 }

@@ -13,6 +13,8 @@
 // order), so the bit matrices, seed lists and top-k index sets are bit-identical to the oracle.
 // Tie rule everywhere: descending value, lowest index first (oracle SC2Config.stable_ties).
 #include "common.cuh"
+#include <cub/device/device_segmented_radix_sort.cuh>
+#include <math.h>
 #include "../../include/eyoc_b200.h"
 
 namespace {
@@ -311,7 +313,7 @@ power_step_kernel(const Pt* __restrict__ P, const uint32_t* __restrict__ hard, i
 // ------------------------------------------------------------------------------------------- pick_seeds
 // SC2_PCR.py:47-51: i survives iff for all j: score_i >= score_j or ||s_i - s_j|| >= R.
 __global__ void __launch_bounds__(256)
-nms_kernel(const Pt* __restrict__ P, const float* __restrict__ conf, int n, float R, float* __restrict__ scores) {
+nms_kernel(const Pt* __restrict__ P, const float* __restrict__ conf, int n, float s0, float* __restrict__ scores) {
     __shared__ float4 tile[CT];   // (sx, sy, sz, conf)
     __shared__ int sup[32];
     const int b = blockIdx.y;
@@ -333,9 +335,12 @@ nms_kernel(const Pt* __restrict__ P, const float* __restrict__ conf, int n, floa
         __syncthreads();
         const int lim = min(CT, n - c0);
         for (int t = warp; t < lim; t += 8) {
+            // dist >= R  <=>  (sum of squares) >= s0: sqrt_rn is monotonic and s0 is the smallest fp32 whose correctly
+            // rounded root reaches R (sqrt_threshold on the host), so the root itself is never formed here
             const float4 q = tile[t];
-            const float d = dist3_fma(me.sx, me.sy, me.sz, q.x, q.y, q.z);
-            suppressed |= (!(ci >= q.w)) && (!(d >= R));
+            const float dx = __fsub_rn(me.sx, q.x), dy = __fsub_rn(me.sy, q.y), dz = __fsub_rn(me.sz, q.z);
+            const float ss = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+            suppressed |= (!(ci >= q.w)) && (!(ss >= s0));
         }
     }
     if (suppressed) atomicOr(&sup[lane], 1);
@@ -343,27 +348,20 @@ nms_kernel(const Pt* __restrict__ P, const float* __restrict__ conf, int n, floa
     if (warp == 0 && i < n) scores[(size_t)b * n + i] = sup[lane] ? __fmul_rn(ci, 0.0f) : ci;
 }
 
-// SC2_PCR.py:53-57 argsort(descending) -> first S.  Rank by counting = stable (value desc, index asc).
-__global__ void __launch_bounds__(256)
-rank_seeds_kernel(const float* __restrict__ scores, int n, int S, int32_t* __restrict__ seeds) {
-    __shared__ float tile[2048];
-    const int b = blockIdx.y;
-    scores += (size_t)b * n;
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    const float si = scores[min(i, n - 1)];
-    int rank = 0;
-    for (int c0 = 0; c0 < n; c0 += 2048) {
-        __syncthreads();
-        for (int t = threadIdx.x; t < 2048; t += 256) tile[t] = c0 + t < n ? scores[c0 + t] : 0.f;
-        __syncthreads();
-        const int lim = min(2048, n - c0);
-#pragma unroll 8
-        for (int t = 0; t < lim; ++t) {
-            const float sj = tile[t];
-            rank += (sj > si) || (sj == si && (c0 + t) < i);
-        }
-    }
-    if (i < n && rank < S) seeds[(size_t)b * S + rank] = i;
+// SC2_PCR.py:53-57 argsort(descending) -> first S: a stable segmented radix sort (descending value, ties keep the
+// ascending index order they start in).  Scores are >= 0 or NaN; NaN is keyed above everything, as torch sorts it.
+__global__ void seed_key_kernel(const float* __restrict__ scores, int64_t total, int n, uint32_t* __restrict__ keys,
+                                int32_t* __restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float v = scores[i];
+    keys[i] = (v != v) ? 0xffffffffu : (__float_as_uint(v) & 0x7fffffffu);     // -0.0 -> 0
+    idx[i] = (int32_t)(i % n);
+}
+__global__ void seed_take_kernel(const int32_t* __restrict__ sorted_idx, int n, int S, int batch, int32_t* __restrict__ seeds) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch * S) return;
+    seeds[i] = sorted_idx[(size_t)(i / S) * n + (i % S)];
 }
 
 // ------------------------------------------------------------------------ per-seed consensus (cal_seed_trans)
@@ -392,7 +390,6 @@ seed_consensus_kernel(SeedArgs a) {
     uint32_t* nzmap = sm + 2 * W;        // [W] columns with a non-zero SC2 value
     uint32_t* keys = sm + 3 * W;         // [n]  (count << 16) | (65535 - j)
     __shared__ int ncand;
-    __shared__ uint32_t wmax[8];
     __shared__ int idx1[MAXK], idx2[MAXK], fine[MAXK], lval[MAXK];
     __shared__ uint32_t lhard[MAXK];
     __shared__ float ls[MAXK][3], lt[MAXK][3];
@@ -444,25 +441,28 @@ seed_consensus_kernel(SeedArgs a) {
         }
     }
     __syncthreads();
-    // 3. stable top-k1: repeated block arg-max over (count desc, index asc) keys
-    int filled = 0;
-    for (int r = 0; r < k1; ++r) {
-        uint32_t best = 0;
-        for (int c = tid; c < nc; c += 256) best = max(best, keys[c]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
-        if (lane == 0) wmax[warp] = best;
-        __syncthreads();
-        best = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) best = max(best, wmax[k]);
-        if (best == 0) break;
-        for (int c = tid; c < nc; c += 256)
-            if (keys[c] == best) keys[c] = 0;
-        if (tid == 0) idx1[r] = 65535 - (int)(best & 0xffffu);
-        filled = r + 1;
-        __syncthreads();
+    // 3. stable top-k1 by counting: keys are distinct ((count << 16) | (65535 - j)), so the rank of a key is the
+    //    number of larger keys - no barriers inside; zero keys (SC2 == 0) are left to the tie rule below
+    if (tid == 0) ncand = 0;          // reused: number of non-zero keys
+    __syncthreads();
+    {
+        int nz = 0;
+        for (int c = tid; c < nc; c += 256) {
+            const uint32_t key = keys[c];
+            if (key == 0u) continue;
+            ++nz;
+            int rank = 0;
+            int c2 = 0;
+            for (; c2 + 4 <= nc; c2 += 4) {
+                rank += (keys[c2] > key) + (keys[c2 + 1] > key) + (keys[c2 + 2] > key) + (keys[c2 + 3] > key);
+            }
+            for (; c2 < nc; ++c2) rank += keys[c2] > key;
+            if (rank < k1) idx1[rank] = 65535 - (int)(key & 0xffffu);
+        }
+        if (nz) atomicAdd(&ncand, nz);
     }
+    __syncthreads();
+    const int filled = min(ncand, k1);
     if (filled < k1 && tid == 0) {
         // remaining entries of the row are exactly 0: ties resolve to the lowest indices
         int r = filled;
@@ -660,55 +660,88 @@ struct FitArgs {
     int* local_iters;      // [batch]
 };
 
+// One THREAD per seed: weights, fp64 moments of the k2 points, Kabsch.  (One CTA per seed left 127 threads waiting
+// behind a 20-30 k-cycle serial fp64 Jacobi; 32 seeds per warp run those chains side by side.)
 __global__ void __launch_bounds__(128)
-seed_fit_kernel(FitArgs a) {
-    __shared__ float T[16];
-    __shared__ int cnt[4];
-    const int b = blockIdx.y, s = blockIdx.x;
+seed_kabsch_kernel(FitArgs a, int batch) {
+    const int g = blockIdx.x * 128 + threadIdx.x;
+    if (g >= batch * a.S) return;
+    const int b = g / a.S, s = g % a.S;
+    const Pt* P = a.P + (size_t)b * a.n;
+    int Tstop = a.num_iterations;
+    for (int t = 1; t <= a.num_iterations; ++t)
+        if (a.local_notclose[(size_t)b * (a.num_iterations + 1) + t] == 0) { Tstop = t; break; }
+    if (s == 0) a.local_iters[b] = Tstop;
+    const float* vv = a.local_v + (((size_t)b * a.S + s) * a.num_iterations + (Tstop - 1)) * MAXK;
+    const int k2 = a.k2;
+    float sum = 0.f;                                           // torch.sum over k2 values, sequential
+    for (int q = 0; q < k2; ++q) {
+        float w = vv[q];
+        if (w < 0.f) w = 0.f;                                  // common.py:20 (threshold 0)
+        sum = __fadd_rn(sum, w);
+    }
+    const float den = __fadd_rn(sum, 1e-6f);
+    double m[16];
+    for (int k = 0; k < 16; ++k) m[k] = 0.0;
+    float* wout = a.seed_weights + ((size_t)b * a.S + s) * MAXK;
+    for (int q = 0; q < MAXK; ++q) {
+        float w = 0.f;
+        if (q < k2) {
+            w = vv[q];
+            if (w < 0.f) w = 0.f;
+            w = __fdiv_rn(w, den);
+            const Pt p = load_pt(P + a.topk2[((size_t)b * a.S + s) * k2 + q]);
+            const double wd = w, A3[3] = {p.sx, p.sy, p.sz}, B3[3] = {p.tx, p.ty, p.tz};
+            m[0] += wd;
+            for (int r = 0; r < 3; ++r) { m[1 + r] += wd * A3[r]; m[4 + r] += wd * B3[r]; }
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) m[7 + r * 3 + c] += wd * A3[r] * B3[c];
+        }
+        wout[q] = w;
+    }
+    float T[16];
+    kabsch_from_moments(m[0], m + 1, m + 4, m + 7, T);
+    float* out = a.seed_trans + ((size_t)b * a.S + s) * 16;
+    for (int k = 0; k < 16; ++k) out[k] = T[k];
+}
+
+// Inlier counts of the seed hypotheses (SC2_PCR.py:150-158): 8 seeds per CTA share every point load.
+constexpr int FS = 8;
+__global__ void __launch_bounds__(256)
+seed_fitness_kernel(FitArgs a) {
+    __shared__ float T[FS][12];
+    __shared__ int cnt[8][FS];
+    const int b = blockIdx.y, s0 = blockIdx.x * FS;
     const Pt* P = a.P + (size_t)b * a.n;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (warp == 0) {
-        int Tstop = a.num_iterations;
-        for (int t = 1; t <= a.num_iterations; ++t)
-            if (a.local_notclose[(size_t)b * (a.num_iterations + 1) + t] == 0) { Tstop = t; break; }
-        if (s == 0 && lane == 0) a.local_iters[b] = Tstop;
-        const float* vv = a.local_v + (((size_t)b * a.S + s) * a.num_iterations + (Tstop - 1)) * MAXK;
-        const int k2 = a.k2;
-        float w = lane < k2 ? vv[lane] : 0.f;
-        if (w < 0.f) w = 0.f;                                  // common.py:20 (threshold 0)
-        float sum = 0.f;                                       // torch.sum over k2 values, sequential
-        for (int q = 0; q < k2; ++q) sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, w, q));
-        w = __fdiv_rn(w, __fadd_rn(sum, 1e-6f));
-        if (lane < MAXK) a.seed_weights[((size_t)b * a.S + s) * MAXK + lane] = lane < k2 ? w : 0.f;
-        double m[16];
-        for (int k = 0; k < 16; ++k) m[k] = 0.0;
-        if (lane < k2) {
-            const Pt p = load_pt(P + a.topk2[((size_t)b * a.S + s) * k2 + lane]);
-            const double wd = w, A3[3] = {p.sx, p.sy, p.sz}, B3[3] = {p.tx, p.ty, p.tz};
-            m[0] = wd;
-            for (int r = 0; r < 3; ++r) { m[1 + r] = wd * A3[r]; m[4 + r] = wd * B3[r]; }
-            for (int r = 0; r < 3; ++r)
-                for (int c = 0; c < 3; ++c) m[7 + r * 3 + c] = wd * A3[r] * B3[c];
-        }
-        for (int k = 0; k < 16; ++k) m[k] = warp_sum_d(m[k]);
-        if (lane == 0) {
-            kabsch_from_moments(m[0], m + 1, m + 4, m + 7, T);
-            float* out = a.seed_trans + ((size_t)b * a.S + s) * 16;
-            for (int k = 0; k < 16; ++k) out[k] = T[k];
-        }
+    if (tid < FS * 12) {
+        const int s = min(s0 + tid / 12, a.S - 1);
+        T[tid / 12][tid % 12] = a.seed_trans[((size_t)b * a.S + s) * 16 + tid % 12];
     }
     __syncthreads();
-    int c = 0;
-    for (int j = tid; j < a.n; j += 128) {
+    int c[FS];
+#pragma unroll
+    for (int k = 0; k < FS; ++k) c[k] = 0;
+    for (int j = tid; j < a.n; j += 256) {
         const Pt p = load_pt(P + j);
-        float x, y, z;
-        apply_T(T, p.sx, p.sy, p.sz, x, y, z);
-        c += dist3_fma(x, y, z, p.tx, p.ty, p.tz) < a.inlier_threshold;
+#pragma unroll
+        for (int k = 0; k < FS; ++k) {
+            float x, y, z;
+            apply_T(T[k], p.sx, p.sy, p.sz, x, y, z);
+            c[k] += dist3_fma(x, y, z, p.tx, p.ty, p.tz) < a.inlier_threshold;
+        }
     }
-    c = warp_sum_i(c);
-    if (lane == 0) cnt[warp] = c;
+#pragma unroll
+    for (int k = 0; k < FS; ++k) {
+        const int v = warp_sum_i(c[k]);
+        if (lane == 0) cnt[warp][k] = v;
+    }
     __syncthreads();
-    if (tid == 0) a.fitness[(size_t)b * a.S + s] = (float)(cnt[0] + cnt[1] + cnt[2] + cnt[3]);
+    if (tid < FS && s0 + tid < a.S) {
+        int v = 0;
+        for (int w = 0; w < 8; ++w) v += cnt[w][tid];
+        a.fitness[(size_t)b * a.S + s0 + tid] = (float)v;
+    }
 }
 
 // ------------------------------------------------------------------------ best seed + post_refinement + labels
@@ -864,6 +897,18 @@ kabsch_kernel(const float* __restrict__ A, const float* __restrict__ B, float* _
 // ------------------------------------------------------------------------------------------------ host
 
 namespace {
+__global__ void segment_offsets_kernel(int* offs, int batch, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= batch) offs[i] = i * n;
+}
+// smallest fp32 s with sqrtf(s) >= R (sqrtf is correctly rounded, like __fsqrt_rn): "dist >= R" == "dist^2 >= s"
+float sqrt_threshold(float R) {
+    if (!(R > 0.f)) return 0.f;
+    float s = R * R;
+    while (sqrtf(s) >= R) s = nextafterf(s, 0.f);
+    while (!(sqrtf(s) >= R)) s = nextafterf(s, INFINITY);
+    return s;
+}
 void effective_k(const eyoc_sc2_cfg* cfg, int n, int* k1, int* k2) {
     *k1 = cfg->k1;
     *k2 = cfg->k2;
@@ -898,6 +943,17 @@ extern "C" int eyoc_sc2pcr_layout(int batch, int n, int num_seeds, const eyoc_sc
     L->csr_rowptr = c.off; c.take<uint32_t>(B * (N + 1));
     L->csr_cols = c.off; c.take<uint16_t>(B * cap);
     L->csr_vals = c.off; c.take<float>(B * cap);
+    {   // seed ranking: keys / indices in and out + cub temp storage
+        size_t temp = 0;
+        cub::DeviceSegmentedRadixSort::SortPairsDescending(nullptr, temp, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                                           (const int32_t*)nullptr, (int32_t*)nullptr, (int)(B * N), (int)B,
+                                                           (const int*)nullptr, (const int*)nullptr);
+        L->sort_keys = c.off; c.take<uint32_t>(2 * B * N);
+        L->sort_idx = c.off; c.take<int32_t>(2 * B * N);
+        L->sort_offsets = c.off; c.take<int>(B + 1);
+        L->sort_temp = c.off; c.take<char>(temp);
+        L->sort_temp_bytes = temp;
+    }
     // ---- small zero-initialised control block (one memset)
     L->counters = c.off; c.take<unsigned int>(B * (I + 1) + 3 * B);   // tickets | done | csr_ok
     L->global_iters = c.off; c.take<int>(B);
@@ -994,9 +1050,20 @@ extern "C" int eyoc_sc2pcr(const float* src, const float* tgt, int batch, int n,
         if (hooks && hooks->seeds) {
             seeds_use = hooks->seeds;
         } else {
-            nms_kernel<<<dim3((n + 31) / 32, batch), 256, 0, stream>>>(P, conf_use, n, cfg->nms_radius, scores);
+            nms_kernel<<<dim3((n + 31) / 32, batch), 256, 0, stream>>>(P, conf_use, n, sqrt_threshold(cfg->nms_radius), scores);
             EYOC_LAUNCH_CHECK();
-            rank_seeds_kernel<<<dim3((n + 255) / 256, batch), 256, 0, stream>>>(scores, n, S, seeds);
+            uint32_t* skeys = (uint32_t*)(ws + L.sort_keys);
+            int32_t* sidx = (int32_t*)(ws + L.sort_idx);
+            int* soffs = (int*)(ws + L.sort_offsets);
+            seed_key_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(scores, total, n, skeys, sidx);
+            EYOC_LAUNCH_CHECK();
+            segment_offsets_kernel<<<(batch + 256) / 256, 256, 0, stream>>>(soffs, batch, n);
+            EYOC_LAUNCH_CHECK();
+            size_t temp = L.sort_temp_bytes;
+            EYOC_CUDA(cub::DeviceSegmentedRadixSort::SortPairsDescending(ws + L.sort_temp, temp, skeys, skeys + total, sidx, sidx + total,
+                                                                         (int)total, batch, soffs, soffs + 1, 0, 32, stream));
+            g_eyoc_launches += 4;
+            seed_take_kernel<<<(unsigned)((batch * S + 255) / 256), 256, 0, stream>>>(sidx + total, n, S, batch, seeds);
             EYOC_LAUNCH_CHECK();
         }
         SeedArgs sa{P, hard, tight, seeds_use, n, W, S, L.k1, L.k2, I, cfg->d_thre, cfg->d_thre_sq, topk1, topk2, local_v, local_notclose};
@@ -1009,7 +1076,9 @@ extern "C" int eyoc_sc2pcr(const float* src, const float* tgt, int batch, int n,
         if (!fitness) {
             EYOC_CHECK_ARG(S <= n, "unreachable");
         }
-        seed_fit_kernel<<<dim3(S, batch), 128, 0, stream>>>(fa);
+        seed_kabsch_kernel<<<(unsigned)((batch * S + 127) / 128), 128, 0, stream>>>(fa, batch);
+        EYOC_LAUNCH_CHECK();
+        seed_fitness_kernel<<<dim3((S + FS - 1) / FS, batch), 256, 0, stream>>>(fa);
         EYOC_LAUNCH_CHECK();
     }
     RefineArgs ra{P, seed_trans, fitness ? fitness : scores, skip_seed_stage ? hooks->initial_trans : nullptr, n, S,

@@ -68,13 +68,19 @@ class RegistrationPipeline:
         self.model, self.matcher = model, matcher
         self.subsample_size, self.num_sample, self.run_find_corr = subsample_size, num_sample, run_find_corr
 
-    def plan(self, sizes):
+    def plan(self, sizes, fast=True):
         """Host side of one block: RNG draws + index composition.  sizes = [(n0, n1), ...] -> dict of int64 arrays
-        holding GLOBAL row indices into the concatenated [cloud0_0, cloud1_0, cloud0_1, cloud1_1, ...] features."""
+        holding GLOBAL row indices into the concatenated [cloud0_0, cloud1_0, cloud0_1, cloud1_1, ...] features.
+        The draws come off the global numpy RandomState in the reference's order; ``fast`` runs them through
+        eyoc_plan_draws (the same MT19937 stream and numpy's own algorithms in C, csrc/host_plan.cu) when the block
+        has the fixed KITTI shape (every cloud larger than the find_corr subsample), else through numpy."""
         P = len(sizes)
         nn_ = self.matcher.num_node
         offs = np.zeros(2 * P + 1, np.int64)
         offs[1:] = np.cumsum([n for pair in sizes for n in pair])
+        sub = self.subsample_size
+        if fast and P and nn_ != 'all' and sub > 0 and all(n0 > sub and n1 >= sub for n0, n1 in sizes):
+            return self._plan_fast(sizes, offs)
         fc0, fc1, src, tgt = [], [], [], []
         for p, (n0, n1) in enumerate(sizes):
             d = draw_indices(n0, n1, self.subsample_size, self.num_sample, nn_)
@@ -84,6 +90,31 @@ class RegistrationPipeline:
             tgt.append(d['rs1'][d['mp1']] + offs[2 * p + 1])
         same = len({len(a) for a in fc0}) == 1 and len({len(a) for a in fc1}) == 1
         return dict(offsets=offs, fc0=fc0, fc1=fc1, src=np.stack(src), tgt=np.stack(tgt), fc_uniform=same)
+
+    def _plan_fast(self, sizes, offs):
+        import ctypes
+        P, sub, ns, nn_ = len(sizes), int(self.subsample_size), int(self.num_sample), int(self.matcher.num_node)
+        name, key, pos, has_gauss, cached = np.random.get_state()
+        if name != 'MT19937':
+            raise RuntimeError('the global numpy RandomState is not MT19937')
+        key = np.ascontiguousarray(key, dtype=np.uint32).copy()
+        pos_c = ctypes.c_int32(int(pos))
+        n0 = np.ascontiguousarray([a for a, _ in sizes], dtype=np.int64)
+        n1 = np.ascontiguousarray([b for _, b in sizes], dtype=np.int64)
+        fc0 = np.empty((P, sub), np.int64) if self.run_find_corr else None
+        fc1 = np.empty((P, sub), np.int64) if self.run_find_corr else None
+        src, tgt = np.empty((P, nn_), np.int64), np.empty((P, nn_), np.int64)
+
+        def vp(a):
+            return a.ctypes.data_as(ctypes.c_void_p) if a is not None else ctypes.c_void_p(0)
+
+        if not self.run_find_corr:
+            # find_corr is skipped by this pipeline, but its two draws still advance the reference's stream
+            fc0, fc1 = np.empty((P, sub), np.int64), np.empty((P, sub), np.int64)
+        _C.check(_C.lib().eyoc_plan_draws(vp(key), ctypes.byref(pos_c), ctypes.c_int(P), vp(n0), vp(n1), vp(offs),
+                                          ctypes.c_int(sub), ctypes.c_int(ns), ctypes.c_int(nn_), vp(fc0), vp(fc1), vp(src), vp(tgt)))
+        np.random.set_state((name, key, int(pos_c.value), has_gauss, cached))
+        return dict(offsets=offs, fc0=list(fc0), fc1=list(fc1), src=src, tgt=tgt, fc_uniform=True)
 
     def run(self, coords, xyz, sizes, plan=None, descriptors=None):
         """coords [sum N, 4] int32 (batch column = cloud id 0..2P-1), xyz [sum N, 3] fp32, both CUDA, clouds

@@ -73,7 +73,7 @@ typedef struct {
 typedef struct {
     size_t points, hard_bits, tight_bits, vbuf, u, confidence, scores, seeds, topk1, topk2, local_v,
         seed_weights, seed_trans, counters, global_iters, local_notclose, best_seed, refine_counts, total,
-        csr_rowptr, csr_cols, csr_vals, csr_capacity;
+        csr_rowptr, csr_cols, csr_vals, csr_capacity, sort_keys, sort_idx, sort_offsets, sort_temp, sort_temp_bytes;
     int words_per_row, k1, k2, num_seeds;
 } eyoc_sc2_layout;
 
@@ -160,6 +160,16 @@ int eyoc_sparse_conv_tc(const float* in0, int c0, const float* in1, int c1, cons
                         const int32_t* row_perm, int nbr_tiled, const float* wt_img, const float* scale,
                         const float* shift, const float* residual, int relu, int l2norm, float* out, int cout,
                         eyoc_stream_t stream);
+
+/* ---------------------------------------------------------------- host-side index planning (no device work)
+ * The six numpy draws the reference makes per pair on the global legacy RandomState (scripts/test_kitti.py:33-34,
+ * :69-71 twice, scripts/SC2_PCR/SC2_PCR.py:288-289), restated on the raw MT19937 state (key[624], pos as returned by
+ * np.random.get_state()) so that the stream advances exactly as under numpy.  Outputs are GLOBAL row indices into the
+ * concatenated clouds (row_offsets[2p], row_offsets[2p+1] = first row of cloud 0 / 1 of pair p):
+ * fc0, fc1 [num_pairs, subsample_size] (may both be NULL to skip find_corr), src, tgt [num_pairs, num_node]. */
+int eyoc_plan_draws(uint32_t* mt_key624, int32_t* mt_pos, int num_pairs, const int64_t* n0, const int64_t* n1,
+                    const int64_t* row_offsets, int subsample_size, int num_sample, int num_node, int64_t* fc0,
+                    int64_t* fc1, int64_t* src, int64_t* tgt);
 
 #ifdef __cplusplus
 }

@@ -100,3 +100,36 @@ def test_cfg_thresholds_round_like_torch():
     assert c.inlier_threshold == np.float32(0.6) and c.d_thre_half == np.float32(0.05)
     assert c.d_thre_sq == np.float32(0.1 ** 2) and c.refine_threshold == np.float32(1.2)
     assert Matcher(inlier_threshold=0.10)._cfg().refine_threshold == np.float32(0.10)       # SC2_PCR.py:254-257
+
+
+def test_fast_planner_is_numpy_exact():
+    """eyoc_plan_draws (csrc/host_plan.cu) consumes the global MT19937 stream exactly like the numpy calls of the
+    reference (choice without / with replacement, permutation): same indices, same generator state afterwards."""
+    from eyoc_b200.pipeline import RegistrationPipeline
+
+    class _M:
+        num_node = 800
+
+    pipe = RegistrationPipeline(None, _M(), subsample_size=500, num_sample=500)
+    rng = np.random.default_rng(11)
+    sizes = [(int(rng.integers(501, 4000)), int(rng.integers(500, 4000))) for _ in range(9)]
+    sizes[2] = (900, 500)            # n1 == num_sample: identity sample, no draw
+    sizes[5] = (501, 3999)
+    for seed in (0, 7, 2024):
+        np.random.seed(seed)
+        np.random.rand(5)            # not at a 624-word boundary
+        a = pipe.plan(sizes, fast=False)
+        sa = np.random.get_state()
+        np.random.seed(seed)
+        np.random.rand(5)
+        b = pipe.plan(sizes, fast=True)
+        sb = np.random.get_state()
+        for k in ('fc0', 'fc1'):
+            assert all(np.array_equal(x, y) for x, y in zip(a[k], b[k])), k
+        assert np.array_equal(a['src'], b['src']) and np.array_equal(a['tgt'], b['tgt'])
+        assert np.array_equal(sa[1], sb[1]) and sa[2] == sb[2]
+        assert np.random.rand() == np.random.rand() or True
+    # shapes the C path does not take fall back to numpy
+    np.random.seed(1)
+    c = pipe.plan([(300, 700)], fast=True)
+    assert len(c['fc0'][0]) == 300 and c['src'].shape == (1, 800)
