@@ -235,7 +235,7 @@ def run_ours(args):
         return rec_host
 
     for _ in range(W):
-        step_resident()
+        allrec, out = step_resident()       # same tensor lifetimes as the timed loop (no allocator growth inside it)
     # ---- device-resident timing (value) + per-kernel events for the roofline
     barrier()
     sampler = ClockSampler(local)
@@ -255,7 +255,7 @@ def run_ours(args):
     launches = int(lib.eyoc_launch_count() - launches0)
     prof, enn.PROFILE = enn.PROFILE, None
     ms = ev0.elapsed_time(ev1)
-    if args.conv_breakdown or world > 1:
+    if True:
         print(f'[rank {rank}] per-step ms: ' + ' '.join(f'{a.elapsed_time(b):.1f}' for a, b in zip(step_ev[:-1], step_ev[1:])),
               file=sys.stderr, flush=True)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -304,7 +304,7 @@ def run_ours(args):
                   f'ms/launch={d[1] / d[0]:8.3f} algGB/s={d[2] / d[1] / 1e6:8.1f} TFLOP/s={d[3] / d[1] / 1e9:7.2f}', file=sys.stderr)
     peak, peak_src = _peaks()
     achieved = tot_bytes / (tot_ms / 1e3) / 1e9 if tot_ms > 0 else 0.0
-    roofline = {'bound': 'hbm', 'kernel': 'sparse_conv_tc_kernel (all tensor-core sparse-conv launches of the timed region)',
+    roofline = {'bound': 'hbm', 'kernel': ('sparse_conv_h_kernel' if enn.CONV_MODE == 'f16x3' else 'sparse_conv_tc_kernel') + ' (all tensor-core sparse-conv launches of the timed region)',
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
                 'peak_source': peak_src, 'launches_timed': n_tiled, 'avg_launch_ms': tot_ms / max(n_tiled, 1),
                 'share_of_step': tot_ms / ms if ms > 0 else None,
@@ -347,7 +347,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--pairs-per-gpu', type=int, default=64)
     ap.add_argument('--descriptors', default='planted', choices=['planted', 'network'])
-    ap.add_argument('--conv-mode', default=None, choices=['fp32', 'tf32x3'])
+    ap.add_argument('--conv-mode', default=None, choices=['fp32', 'tf32x3', 'f16x3'])
     ap.add_argument('--cpu-pairs', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--conv-breakdown', action='store_true')

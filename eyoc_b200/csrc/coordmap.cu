@@ -170,13 +170,14 @@ __global__ void scan_sums_kernel(int* block_sums, int nblocks, int* total) {   /
 // pass 3: emit coarse coordinates in first-occurrence order and point the hash at the coarse row
 __global__ void down_emit_kernel(const int* __restrict__ coords, int n, int ts_out, const int* __restrict__ flag,
                                  const int* __restrict__ pos, const int* __restrict__ block_sums, unsigned long long* keys, int* vals,
-                                 long long cap, int* __restrict__ coords_out) {
+                                 long long cap, int* __restrict__ coords_out, int* __restrict__ sel_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !flag[i]) return;
     const int4 c = reinterpret_cast<const int4*>(coords)[i];
     const int4 cc = make_int4(c.x, floor_to(c.y, ts_out), floor_to(c.z, ts_out), floor_to(c.w, ts_out));
     const int row = pos[i] + block_sums[i / SCAN_B];
     reinterpret_cast<int4*>(coords_out)[row] = cc;
+    if (sel_out) sel_out[row] = i;
     const unsigned long long key = pack4(cc.x, cc.y, cc.z, cc.w);
     long long slot = (long long)(mix64(key) & (unsigned long long)(cap - 1));
     while (keys[slot] != key) slot = (slot + 1) & (cap - 1);
@@ -196,6 +197,21 @@ __global__ void kernel_map_kernel(const int* __restrict__ out_coords, int n_out,
     int v = -1;
     if (in_range16(x) && in_range16(y) && in_range16(z)) v = hash_lookup(keys, vals, cap, pack4(c.x, x, y, z));
     nbr[(size_t)k * n_out + o] = v;
+}
+
+// Voxelisation (lib/data_loaders.py:936-979): q = floor(xyz / voxel_size) evaluated as torch / numpy do in fp32 (true
+// division, then floor), batch column from the optional per-point cloud index.  status bit 0: outside the 16-bit range.
+__global__ void quantize_kernel(const float* __restrict__ xyz, const int* __restrict__ cloud, int n, float voxel_size,
+                                int* __restrict__ q, int* status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float fx = floorf(__fdiv_rn(xyz[3 * (size_t)i], voxel_size)), fy = floorf(__fdiv_rn(xyz[3 * (size_t)i + 1], voxel_size)),
+                fz = floorf(__fdiv_rn(xyz[3 * (size_t)i + 2], voxel_size));
+    const int b = cloud ? cloud[i] : 0;
+    const bool ok = fx >= -32768.f && fx <= 32767.f && fy >= -32768.f && fy <= 32767.f && fz >= -32768.f && fz <= 32767.f &&
+                    b >= 0 && b <= 65535;
+    if (!ok) atomicOr(status, 1);
+    reinterpret_cast<int4*>(q)[i] = ok ? make_int4(b, (int)fx, (int)fy, (int)fz) : make_int4(0, 0, 0, 0);
 }
 
 // Stride-1 map of a coordinate set onto itself: offsets come in mirrored pairs (k, K^3-1-k) and i = nbr[k, o] <=>
@@ -348,7 +364,47 @@ extern "C" int eyoc_coords_downsample(const int32_t* coords, int64_t n, int ts_o
     scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, nb, n_out);
     EYOC_LAUNCH_CHECK();
     down_emit_kernel<<<g, 256, 0, stream>>>(coords, (int)n, ts_out, flag, pos, sums, (unsigned long long*)table_keys, table_vals, capacity,
-                                            coords_out);
+                                            coords_out, nullptr);
+    EYOC_LAUNCH_CHECK();
+    return EYOC_OK;
+}
+
+extern "C" size_t eyoc_voxelize_workspace_bytes(int64_t n) {
+    return eyoc_align((size_t)n * 16) + eyoc_downsample_workspace_bytes(n);
+}
+
+extern "C" int eyoc_voxelize(const float* xyz, const int32_t* cloud, int64_t n, float voxel_size, uint64_t* table_keys,
+                             int32_t* table_vals, int64_t capacity, int32_t* coords_out, int32_t* sel_out, int32_t* n_out,
+                             int32_t* status, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    EYOC_CHECK_ARG(xyz && table_keys && table_vals && coords_out && sel_out && n_out && status, "eyoc_voxelize: null argument");
+    EYOC_CHECK_ARG(n >= 0 && n < (1ll << 31) && voxel_size > 0.f, "eyoc_voxelize: bad n / voxel size");
+    EYOC_CHECK_ARG(capacity >= 2 * n && capacity >= 2 && (capacity & (capacity - 1)) == 0, "eyoc_voxelize: capacity must be a power of two >= 2n");
+    if (workspace == nullptr || workspace_bytes < eyoc_voxelize_workspace_bytes(n)) {
+        eyoc_set_error("eyoc_voxelize: workspace too small");
+        return EYOC_ERR_WORKSPACE;
+    }
+    hash_clear_kernel<<<(unsigned)((capacity + 255) / 256), 256, 0, stream>>>((unsigned long long*)table_keys, table_vals, capacity);
+    EYOC_LAUNCH_CHECK();
+    if (n == 0) { EYOC_CUDA(cudaMemsetAsync(n_out, 0, 4, stream)); return EYOC_OK; }
+    WsCarver c(workspace, workspace_bytes);
+    int* q = c.take<int>(4 * n);
+    int* flag = c.take<int>(n);
+    int* pos = c.take<int>(n);
+    const int nb = (int)((n + SCAN_B - 1) / SCAN_B);
+    int* sums = c.take<int>(nb + 1);
+    const unsigned g = (unsigned)((n + 255) / 256);
+    quantize_kernel<<<g, 256, 0, stream>>>(xyz, cloud, (int)n, voxel_size, q, status);
+    EYOC_LAUNCH_CHECK();
+    down_insert_kernel<<<g, 256, 0, stream>>>(q, (int)n, 1, (unsigned long long*)table_keys, table_vals, capacity);
+    EYOC_LAUNCH_CHECK();
+    down_flag_kernel<<<g, 256, 0, stream>>>(q, (int)n, 1, (const unsigned long long*)table_keys, table_vals, capacity, flag);
+    EYOC_LAUNCH_CHECK();
+    scan_block_kernel<<<nb, SCAN_B, 0, stream>>>(flag, (int)n, pos, sums);
+    EYOC_LAUNCH_CHECK();
+    scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, nb, n_out);
+    EYOC_LAUNCH_CHECK();
+    down_emit_kernel<<<g, 256, 0, stream>>>(q, (int)n, 1, flag, pos, sums, (unsigned long long*)table_keys, table_vals, capacity, coords_out,
+                                            sel_out);
     EYOC_LAUNCH_CHECK();
     return EYOC_OK;
 }

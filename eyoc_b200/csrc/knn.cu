@@ -28,6 +28,26 @@ __device__ __forceinline__ unsigned long long pack_key(float v, int j) {
     return ((unsigned long long)enc << 32) | (unsigned int)j;
 }
 
+// Packed fp32 pairs (sm_100 fma/sub .f32x2): two independent round-to-nearest fp32 operations per instruction - the
+// per-element arithmetic (and so every result bit) is that of the scalar instructions, at half the issue slots.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 // distance value the reference compares, from the raw accumulator
 template <int FORM>
 __device__ __forceinline__ float value_of(float a) {
@@ -81,11 +101,11 @@ knn1_kernel(const float* __restrict__ Q, const float* __restrict__ R, int nq, in
     const int tile1 = min(ntiles_total, tile0 + tiles_per_split);
     for (int t = tile0; t < tile1; ++t) {
         const int r0 = t * TR;
-        float acc[8][8];
+        f32x2 acc2[8][4];            // acc2[i][jp] = accumulators of columns (2 jp, 2 jp + 1)
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+            for (int j = 0; j < 4; ++j) acc2[i][j] = 0ull;
         for (int cc = 0; cc < dimp; cc += TC) {
             __syncthreads();
             for (int r = tid & 127; r < TR; r += 128) {
@@ -114,20 +134,27 @@ knn1_kernel(const float* __restrict__ Q, const float* __restrict__ R, int nq, in
                 const float4 ra = *reinterpret_cast<const float4*>(Rs + c * TR + tx * 4);
                 const float4 rb = *reinterpret_cast<const float4*>(Rs + c * TR + 64 + tx * 4);
                 const float q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-                const float r[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                const f32x2 r2[4] = {pack2(ra.x, ra.y), pack2(ra.z, ra.w), pack2(rb.x, rb.y), pack2(rb.z, rb.w)};
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < 8; ++i) {
+                    const f32x2 q2 = pack2(q[i], q[i]);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < 4; ++j) {
                         if (FORM == 0) {
-                            const float d = __fsub_rn(q[i], r[j]);
-                            acc[i][j] = __fmaf_rn(d, d, acc[i][j]);
+                            const f32x2 d = sub2(q2, r2[j]);
+                            acc2[i][j] = fma2(d, d, acc2[i][j]);
                         } else {
-                            acc[i][j] = __fmaf_rn(q[i], r[j], acc[i][j]);
+                            acc2[i][j] = fma2(q2, r2[j], acc2[i][j]);
                         }
                     }
+                }
             }
         }
+        float acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) unpack2(acc2[i][j], acc[i][2 * j], acc[i][2 * j + 1]);
         // running argmin; this thread visits its columns in ascending j, so strict '<' keeps the first.
         // Fast reject on the raw accumulator: form 1's  sqrt((2 - 2 acc) + 1e-6)  is monotonically non-increasing in
         // acc (every rounding step is monotonic), so a candidate can only win when acc > the winner's acc; the exact

@@ -1,0 +1,742 @@
+// Sparse convolution on the 5th-generation tensor cores, fp16 hi/lo split data path ("f16x3"), sm_100a only.
+//
+// Same operator and fused epilogue as csrc/sparse_conv.cu / csrc/sparse_conv_tc.cu (ME.MinkowskiConvolution[Transpose]
+// + BN + ReLU + residual + ME.cat + L2 norm of model/resunet.py:142-193); what changes is the operand format and the
+// pipeline.  csrc/sparse_conv_tc.cu (tf32x3) spends, per 256-row x 32-channel work item, 8 MMAs (1 140 cycles), 192 KB
+// of shared-memory traffic (gather landing + x_lo pass + both operand reads) and a proxy fence per producer thread that
+// drains the thread's outstanding index load.  Here:
+//   * activations live in HBM in the SPLIT-HALF format: per row and 32-channel chunk 128 bytes = 32 fp16 "hi" values
+//     followed by 32 fp16 "lo'" values, x = hi + lo' * 2^-11 (22 significant bits, the same as a tf32 hi/lo pair, same
+//     bytes per row as fp32).  A gathered 128-byte row chunk IS the K-major SWIZZLE_128B operand row of 64 "virtual"
+//     fp16 channels: no conversion pass, no second copy in shared memory;
+//   * weights are pre-scaled by a power of two (max |w'| in [2^13, 2^14)), split w' = hi + lo and laid out per
+//     (offset, chunk) as rows [W_hi | W_hi 2^-11] (and [W_lo | W_lo 2^-11] on the stacked M lanes), so that FOUR
+//     kind::f16 MMAs (K = 16 each) per item give (W_hi + W_lo)(x_hi + x_lo) for C_out <= 64 (hi on lanes 0-63, lo on
+//     lanes 64-127, summed in the epilogue) and SIX give W_hi x_hi + W_hi x_lo + W_lo x_hi for 128 output channels;
+//     fp16 x fp16 products are exact in the fp32 accumulator;
+//   * 16 producer warps in 2 groups that take the items in turn, one MMA-issuing thread per accumulator tile; a stage is handed over with
+//     cp.async.mbarrier.arrive.noinc - the "full" barrier counts each lane's copies as they land (the CUTLASS sm100
+//     cp.async mainloop's hand-over; the proxy fence is issued by the MMA thread), so no producer ever waits on its own
+//     copies or on an index load (the next item's indices are prefetched into a second named register set);
+//   * the epilogue writes split-half rows again (or fp32 for the network output).
+// Work items, tile order, weight slabs by TMA bulk copy and the TMEM accumulator layout (2 tiles x 256 columns) are those
+// of the tf32 kernel.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "../../include/eyoc_b200.h"
+
+using namespace tcp;
+
+namespace {
+
+constexpr int TR = 256;        // output rows per accumulator tile (UMMA N)
+constexpr int KC = 32;         // channels per chunk: 32 hi + 32 lo' fp16 = one 128-byte swizzle-atom row
+constexpr int NTILE = 2;       // accumulator tiles per CTA: 2 x 256 TMEM columns
+constexpr int NPW = 16;        // producer warps, in NG groups that take the work items in turn (also the epilogue warps)
+constexpr int NG = 2;          // groups: a warp has about 16 cp.async in flight at most, so bandwidth needs many warps,
+                               // and several items in the making at once hide the per-item latency chain
+constexpr int WPG = NPW / NG;  // warps per group
+constexpr int RPW = 256 / WPG; // tile rows a warp gathers per item
+constexpr int NI = RPW / 32;   // neighbour indices per lane and item
+constexpr int NPT = NPW * 32;
+constexpr int XS_BYTES = TR * 128;             // 32 KB per stage
+constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
+
+__device__ __forceinline__ void xh_split(float x, __half& hi, __half& lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(__fmul_rn(__fsub_rn(x, __half2float(hi)), LO_SCALE));
+}
+__device__ __forceinline__ float xh_join(__half hi, __half lo) { return __fmaf_rn(__half2float(lo), LO_INV, __half2float(hi)); }
+
+// 8 consecutive channels of a split-half row: 16 bytes of hi, 16 bytes of lo' 64 bytes further
+__device__ __forceinline__ void xh_load8(const uint8_t* row, int col, float* y) {
+    const uint8_t* p = row + (col >> 5) * 128 + (col & 31) * 2;
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint4 l = __ldg(reinterpret_cast<const uint4*>(p + 64));
+    const __half2* hh = reinterpret_cast<const __half2*>(&h);
+    const __half2* ll = reinterpret_cast<const __half2*>(&l);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        y[2 * i] = xh_join(__low2half(hh[i]), __low2half(ll[i]));
+        y[2 * i + 1] = xh_join(__high2half(hh[i]), __high2half(ll[i]));
+    }
+}
+__device__ __forceinline__ void xh_store8(uint8_t* row, int col, const float* y) {
+    uint8_t* p = row + (col >> 5) * 128 + (col & 31) * 2;
+    uint4 h, l;
+    __half2* hh = reinterpret_cast<__half2*>(&h);
+    __half2* ll = reinterpret_cast<__half2*>(&l);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __half h0, l0, h1, l1;
+        xh_split(y[2 * i], h0, l0);
+        xh_split(y[2 * i + 1], h1, l1);
+        hh[i] = __halves2half2(h0, h1);
+        ll[i] = __halves2half2(l0, l1);
+    }
+    *reinterpret_cast<uint4*>(p) = h;
+    *reinterpret_cast<uint4*>(p + 64) = l;
+}
+
+struct HArgs {
+    const uint8_t* in0; int c0;       // split-half rows: 4 * c bytes per row
+    const uint8_t* in1; int c1;
+    const int32_t* nbr;               // [K, n_out]; column = output row, or tile position when nbr_tiled
+    const int32_t* row_perm;          // [n_out] tile position -> output row, or null
+    const uint32_t* tile_masks;       // [ceil(n_out / 256)] offsets with a neighbour per tile, or null (computed here)
+    const __half* wt_img;             // per (k, chunk, part) one slab: swizzled shared-memory image
+    const float* scale;
+    const float* shift;
+    const uint8_t* residual; int residual_packed;
+    uint8_t* out; int out_packed;
+    float acc_scale;                  // 2^-a: undoes the power-of-two weight pre-scale
+    int K, n_out, cout, relu, l2norm, nbr_tiled;
+};
+
+// Debug / measurement only (tools/conv_ablate.py): bit 0 = skip the MMAs, bit 1 = skip the gather copies, bit 2 = skip
+// the weight-slab copies, bit 3 = record per-CTA phase timestamps.  Results are garbage when bits 0-2 are set.
+__device__ int g_ablate = 0;
+__device__ long long g_times[1024][6];
+// bit 4: CTAs 200..203 trace their first 96 items: [cta][item][0..2] the item's producer warp (empty wait start / end /
+// copies issued), [3..5] MMA thread (full wait start / end / after commit)
+__device__ long long g_trace[4][96][6];
+
+constexpr int MAX_ITEMS = 27 * 12 * NTILE;      // (kernel offset, 32-channel chunk, tile) work items per CTA
+
+// Work item: bits [0,5) kernel offset, [5,9) chunk index, bit 9 tile, bit 12 = first item of its (offset, chunk),
+// i.e. the MMA side must switch to the next weight slab; bits [13,16) operand stage, bit 10 parity of the stage's "full"
+// barrier for this use.
+__device__ __forceinline__ int item_k(uint32_t it) { return it & 31; }
+__device__ __forceinline__ int item_c(uint32_t it) { return (it >> 5) & 15; }
+__device__ __forceinline__ int item_t(uint32_t it) { return (it >> 9) & 1; }
+__device__ __forceinline__ bool item_first(uint32_t it) { return (it >> 12) & 1; }
+__device__ __forceinline__ uint32_t item_stage(uint32_t it) { return (it >> 13) & 7u; }
+__device__ __forceinline__ uint32_t item_parity(uint32_t it) { return (it >> 10) & 1u; }
+
+__device__ __forceinline__ void bar_sync_producers() { asm volatile("bar.sync 1, %0;" ::"n"(NPT) : "memory"); }
+
+// WIDE = false: C_out <= 64, W_hi / W_lo stacked along M (64 lanes each), 4 MMAs per item.  WIDE = true: 128 output
+// channels per CTA (blockIdx.y selects the half when C_out = 256), W_hi and W_lo are separate 128-row operands, 6 MMAs.
+// Thread map: 16 producer warps (also the epilogue), one weight-loader warp, two MMA-issuer warps (one elected thread each).
+template <bool WIDE, int NSW, int NXS>
+__global__ void __launch_bounds__(NPT + 96, 1)
+sparse_conv_h_kernel(HArgs a) {
+    constexpr bool PER_TILE = !WIDE;                          // one MMA-issuing thread per tile (see "MMA issuers")
+    constexpr int NMMA = PER_TILE ? NTILE : 1;                // MMA-issuing threads
+    // The producers' and issuers' waits test one parity bit, so nobody may run two phases ahead of a barrier.  With one
+    // issuer, commits are in list order and a group that passed item i - NG (stage freed by item i - NG - NXS) knows item
+    // i - 2 NXS is long committed.  With two issuers the commits of the two tiles interleave, but the weight-slab ring
+    // keeps the issuers within NSW slabs = at most 3 list positions of each other: NXS - NG > 3 keeps the argument intact.
+    static_assert(!PER_TILE || (NXS - NG > 3 && NSW == 2), "stage ring too shallow for two issuers");
+    constexpr int W_BYTES = (WIDE ? 256 : 128) * 128;         // slab: 128 (hi 64 | lo 64) or 256 (hi 128 | lo 128) rows of 128 B
+    // instruction descriptor: D = fp32 (bit 4), A = B = fp16 (format 0), both K-major, N = 256, M = 128
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TR >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_off = ((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw);      // 0: declared aligned
+    const uint32_t sX = smem_u32(smem_raw) + smem_off;           // NXS stages; reused by the epilogue transpose
+    const uint32_t sW = sX + NXS * XS_BYTES;                     // NSW slabs
+    float* const sOut = reinterpret_cast<float*>(smem_raw + smem_off);
+    __shared__ uint64_t bars[2 * NXS + 2 * NSW + 1];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ uint32_t valid[NTILE];
+    __shared__ uint32_t tmask[32];
+    __shared__ uint16_t pair_off[27 * 12 + 1];
+    __shared__ uint16_t items[MAX_ITEMS];
+    __shared__ int nitems_s;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long t_start = clock64();
+    const int cin = a.c0 + a.c1;
+    const int nch = cin / KC;
+    const int nparts = WIDE ? a.cout / 128 : 1;
+    const int part = WIDE ? blockIdx.y : 0;
+    const int cpart = WIDE ? 128 : a.cout;                       // output channels this CTA produces
+    const uint32_t a_full = smem_u32(&bars[0]), a_empty = smem_u32(&bars[NXS]);
+    const uint32_t w_full = smem_u32(&bars[2 * NXS]), w_empty = smem_u32(&bars[2 * NXS + NSW]);
+    const uint32_t done_bar = smem_u32(&bars[2 * NXS + 2 * NSW]);
+    const int wload_warp = NPW, mma_warp = NPW + 1;
+    const int tile0 = blockIdx.x * NTILE;
+    const int ntiles = (a.n_out + TR - 1) / TR;
+
+    if (tid == 0) {
+        for (int i = 0; i < NXS; ++i) { mbar_init(a_full + 8 * i, 32 * WPG); mbar_init(a_empty + 8 * i, 1); }
+        for (int i = 0; i < NSW; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, NMMA); }
+        mbar_init(done_bar, NMMA);
+        mbar_init_fence();
+    }
+    if (tid < NTILE) {
+        uint32_t m = 0;
+        if (a.nbr == nullptr) m = tile0 + tid < ntiles ? 1u : 0u;
+        else if (a.tile_masks && tile0 + tid < ntiles) m = __ldg(a.tile_masks + tile0 + tid);
+        valid[tid] = m;
+    }
+    if (warp == mma_warp) tmem_alloc(smem_u32(&tmem_base_s), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    // ---- which kernel offsets have a neighbour in each tile (only when the caller did not precompute the masks)
+    if (a.nbr != nullptr && a.tile_masks == nullptr) {
+        if (tid < TR) {
+#pragma unroll 1
+            for (int t = 0; t < NTILE; ++t) {
+                const int rr = (tile0 + t) * TR + tid;
+                int col = -1;
+                if (rr < a.n_out) col = (a.row_perm && !a.nbr_tiled) ? a.row_perm[rr] : rr;
+                uint32_t m = 0;
+                if (col >= 0) {
+                    int v[27];
+#pragma unroll
+                    for (int k = 0; k < 27; ++k) v[k] = k < a.K ? __ldg(a.nbr + (size_t)k * a.n_out + col) : -1;
+#pragma unroll
+                    for (int k = 0; k < 27; ++k) m |= (uint32_t)(v[k] >= 0) << k;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+                if (lane == 0 && m) atomicOr(&valid[t], m);
+            }
+        }
+        __syncthreads();
+    }
+    // ---- the CTA's ordered work list: (offset, chunk) outer, tiles inner
+    if (tid < 32) {
+        uint32_t m = 0;
+        if (tid < a.K)
+            for (int t = 0; t < NTILE; ++t) m |= ((valid[t] >> tid) & 1u) << t;
+        tmask[tid] = m;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int npairs = a.K * nch;
+        int carry = 0;
+        for (int p0 = 0; p0 < npairs; p0 += 32) {
+            const int p = p0 + lane;
+            const int c = p < npairs ? __popc(tmask[p / nch]) : 0;
+            int x = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            if (p < npairs) pair_off[p] = (uint16_t)(carry + x - c);
+            carry += __shfl_sync(0xffffffffu, x, 31);
+        }
+        if (lane == 0) nitems_s = carry;
+    }
+    __syncthreads();
+    for (int p = tid; p < a.K * nch; p += blockDim.x) {
+        const int k = p / nch, ci = p % nch;
+        uint32_t m = tmask[k];
+        int o = pair_off[p];
+        bool first = true;
+        while (m) {
+            const int t = __ffs(m) - 1;
+            m &= m - 1;
+            items[o++] = (uint16_t)(k | (ci << 5) | (t << 9) | ((first ? 1 : 0) << 12));
+            first = false;
+        }
+    }
+    __syncthreads();
+    const int nitems = nitems_s;
+    // ---- operand stage of every item: one ring of NXS stages in list order
+    for (int i = tid; i < nitems; i += blockDim.x)
+        items[i] = (uint16_t)(items[i] | (((uint32_t)(i / NXS) & 1u) << 10) | ((uint32_t)(i % NXS) << 13));
+    __syncthreads();
+    const int ablate = g_ablate;
+    const bool timing = (ablate & 8) && tid == 0 && blockIdx.x < 1024 && blockIdx.y == 0;
+    const bool tracing = (ablate & 16) && blockIdx.x >= 200 && blockIdx.x < 204 && blockIdx.y == 0;
+    const int tcta = blockIdx.x - 200;
+    if (timing) { g_times[blockIdx.x][0] = t_start; g_times[blockIdx.x][1] = clock64(); g_times[blockIdx.x][5] = nitems; }
+
+    if (tid < NPT) {
+        // =========================================================== producers: async gather -> operand stage
+        // Group g (WPG warps) gathers items g, g + NG, g + 2 NG, ...: warp wg of the group the tile rows [wg RPW, (wg+1) RPW).
+        // NG <= NXS, so a group is never a whole ring ahead of the MMA warp and its parity waits cannot alias.
+        // 8 lanes cover one 128-byte row chunk (coalesced 128-byte requests, conflict-free shared-memory writes):
+        // lane = (rsub, c), pass q handles tile row p = rbase + 4 q + rsub, 16-byte chunk c of the row lands at
+        // p * 128 + ((c ^ (p & 7)) << 4), the SWIZZLE_128B K-major layout the MMA descriptors expect.
+        // Hand-over: cp.async.mbarrier.arrive.noinc - the stage's "full" barrier (32 WPG expected arrivals) receives each
+        // lane's arrival when that lane's copies have landed; no warp waits on its own copies or issues a proxy fence.
+        const int c = lane & 7, rsub = lane >> 3;
+        const int grp = warp / WPG, rbase = (warp % WPG) * RPW;
+        const uint32_t st0 = sX + (uint32_t)(rbase + rsub) * 128u + (uint32_t)((c ^ rsub) << 4);        // q even: p & 7 = rsub
+        const uint32_t st1 = sX + (uint32_t)(rbase + rsub) * 128u + (uint32_t)((c ^ rsub ^ 4) << 4);    // q odd:  p & 7 = rsub + 4
+        const bool identity = a.nbr == nullptr;
+        const bool perm_cols = a.row_perm && !(a.nbr && a.nbr_tiled);
+        const uint32_t cs0 = (uint32_t)a.c0 * 4u, cs1 = (uint32_t)a.c1 * 4u;
+        const int nch0 = a.c0 / KC;
+        // neighbour indices of the warp's RPW rows of item i: lane l holds rows rbase + l (+ 32 j)
+        auto load_item = [&](int i, int (&idx)[NI]) {
+#pragma unroll
+            for (int j = 0; j < NI; ++j) idx[j] = -1;
+            if (i >= nitems) return;
+            const uint32_t it = items[i];
+            const int rr0 = (tile0 + item_t(it)) * TR + rbase + lane;
+            const int32_t* tab = identity ? nullptr : a.nbr + (size_t)item_k(it) * a.n_out;
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                const int rr = rr0 + 32 * j;
+                if (rr < a.n_out) {
+                    const int col = perm_cols ? __ldg(a.row_perm + rr) : rr;
+                    idx[j] = identity ? col : __ldg(tab + col);
+                }
+            }
+        };
+        // rows without a neighbour are zero-filled by the copy itself (source size 0)
+        auto copy_item = [&](int i, const int (&idx)[NI]) {
+            const uint32_t it = items[i];
+            const uint32_t s = item_stage(it);
+            if (tracing && (warp % WPG) == 0 && lane == 0 && i < 96) g_trace[tcta][i][0] = clock64();
+            if (lane == 0) mbar_wait(a_empty + 8 * s, item_parity(it) ^ 1u);        // the MMAs that last read the stage have completed
+            if (tracing && (warp % WPG) == 0 && lane == 0 && i < 96) g_trace[tcta][i][1] = clock64();
+            __syncwarp();
+            if (!(ablate & 2)) {
+                const int ci = item_c(it);
+                const bool first = ci < nch0;
+                const uint8_t* src = (first ? a.in0 : a.in1) + (first ? ci : ci - nch0) * 128 + c * 16;
+                const uint32_t cs = first ? cs0 : cs1;
+                const uint32_t stage_off = s * (uint32_t)XS_BYTES;
+#pragma unroll
+                for (int q = 0; q < RPW / 4; ++q) {
+                    const int v = __shfl_sync(0xffffffffu, idx[q >> 3], ((q & 7) << 2) | rsub);
+                    const uint8_t* ptr = src + (uint64_t)(uint32_t)max(v, 0) * cs;
+                    const uint32_t dst = ((q & 1) ? st1 : st0) + stage_off + (uint32_t)q * 512u;
+                    cp_async16(dst, ptr, v >= 0 ? 16u : 0u);
+                }
+            }
+            cp_async_arrive_noinc(a_full + 8 * s);
+            if (tracing && (warp % WPG) == 0 && lane == 0 && i < 96) g_trace[tcta][i][2] = clock64();
+        };
+        // Output row of tile row `tid` of each tile, for the epilogue (loaded here so that its latency is long gone).
+        int orow[NTILE];
+#pragma unroll
+        for (int t = 0; t < NTILE; ++t) {
+            const int rr = (tile0 + t) * TR + (tid & (TR - 1));
+            orow[t] = rr < a.n_out ? (a.row_perm ? __ldg(a.row_perm + rr) : rr) : -1;
+        }
+        // The group's items: every NG-th of the list.  The indices of the group's next item are fetched, into the other
+        // NAMED register set, before the copies of the current one are issued (rotating registers through moves would
+        // stall on the in-flight load).
+        auto next_own = [&](int from) -> int { return from < 0 ? grp : from + NG; };
+        {
+            int ia[NI], ib[NI];
+            int i = next_own(-1);
+            load_item(i, ia);
+            while (i < nitems) {
+                const int i1 = next_own(i);
+                load_item(i1, ib);
+                copy_item(i, ia);
+                if (i1 >= nitems) break;
+                i = next_own(i1);
+                load_item(i, ia);
+                copy_item(i1, ib);
+            }
+        }
+        // =========================================================== epilogue: TMEM -> smem transpose -> global
+        if (timing) g_times[blockIdx.x][2] = clock64();
+        mbar_wait(done_bar, 0);
+        if (timing) g_times[blockIdx.x][3] = clock64();
+        tc_fence_after();
+        const int q4 = warp & 3;                 // TMEM lane quadrant this warp may read
+        const int cw = warp >> 2;                // which 64 of the tile's 256 columns (rows) this warp moves
+        const int c8n = cpart >> 3;              // 8-channel groups per output row
+        // channel held by this lane; "lo" lanes (W_lo x partial sums, non-WIDE only) go to a second buffer
+        int ch; bool is_lo;
+        if (WIDE) { ch = q4 * 32 + lane; is_lo = false; }
+        else { ch = (q4 & 1) * 32 + lane; is_lo = q4 >= 2; }
+        const bool active = ch < cpart;
+        float* const sOutLo = sOut + TR * cpart;                  // non-WIDE: 2 x (256 rows x cout) fp32 <= 128 KB
+        int* const sRow = reinterpret_cast<int*>(smem_raw + smem_off + 131072);      // output rows of the tile, behind the buffers
+        const size_t row_bytes = (size_t)a.cout * 4;
+        for (int t = 0; t < NTILE; ++t) {
+            if ((tile0 + t) * TR >= a.n_out) break;
+            const bool started = valid[t] != 0 && nitems > 0;
+            if (active) {
+                float* const dstbuf = is_lo ? sOutLo : sOut;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t v[32];
+                    if (started) {
+                        const uint32_t ta = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(t * TR + cw * 64 + c0);
+                        tmem_ld16_nowait(ta, v);
+                        tmem_ld16_nowait(ta + 16, v + 16);
+                        tmem_ld_wait();
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0u;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) dstbuf[(size_t)(cw * 64 + c0 + j) * cpart + ch] = __uint_as_float(v[j]);
+                }
+            }
+            if (tid < TR) sRow[tid] = t ? orow[1] : orow[0];
+            bar_sync_producers();
+            // row-major pass: fused epilogue + coalesced stores; one 8-channel group per thread and unit, 2 units per step
+            // (the residual loads of a step are in flight together)
+            const int total = TR * c8n;
+#pragma unroll 1
+            for (int e0 = 0; e0 < total; e0 += 2 * NPT) {           // total is a multiple of 2 * NPT (c8n = 4, 8 or 16)
+                int rowv[2]; uint4 resh[2], resl[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int e = e0 + u * NPT + tid;
+                    rowv[u] = sRow[e / c8n];
+                    const int col = part * 128 + (e % c8n) * 8;
+                    resh[u] = make_uint4(0u, 0u, 0u, 0u);
+                    resl[u] = resh[u];
+                    if (a.residual && rowv[u] >= 0) {
+                        const uint8_t* rrow = a.residual + (size_t)rowv[u] * row_bytes;
+                        if (a.residual_packed) {
+                            const uint8_t* p = rrow + (col >> 5) * 128 + (col & 31) * 2;
+                            resh[u] = __ldg(reinterpret_cast<const uint4*>(p));
+                            resl[u] = __ldg(reinterpret_cast<const uint4*>(p + 64));
+                        } else {
+                            resh[u] = __ldg(reinterpret_cast<const uint4*>(rrow + (size_t)col * 4));
+                            resl[u] = __ldg(reinterpret_cast<const uint4*>(rrow + (size_t)col * 4 + 16));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int e = e0 + u * NPT + tid;
+                    const int r = e / c8n, cq = e - r * c8n;
+                    const int col = part * 128 + cq * 8;
+                    float y[8], res[8];
+                    {
+                        const float4 y0 = *reinterpret_cast<const float4*>(sOut + (size_t)r * cpart + cq * 8);
+                        const float4 y1 = *reinterpret_cast<const float4*>(sOut + (size_t)r * cpart + cq * 8 + 4);
+                        y[0] = y0.x; y[1] = y0.y; y[2] = y0.z; y[3] = y0.w; y[4] = y1.x; y[5] = y1.y; y[6] = y1.z; y[7] = y1.w;
+                    }
+                    if (!WIDE) {
+                        const float4 z0 = *reinterpret_cast<const float4*>(sOutLo + (size_t)r * cpart + cq * 8);
+                        const float4 z1 = *reinterpret_cast<const float4*>(sOutLo + (size_t)r * cpart + cq * 8 + 4);
+                        y[0] = __fadd_rn(y[0], z0.x); y[1] = __fadd_rn(y[1], z0.y); y[2] = __fadd_rn(y[2], z0.z); y[3] = __fadd_rn(y[3], z0.w);
+                        y[4] = __fadd_rn(y[4], z1.x); y[5] = __fadd_rn(y[5], z1.y); y[6] = __fadd_rn(y[6], z1.z); y[7] = __fadd_rn(y[7], z1.w);
+                    }
+                    if (a.residual_packed) {
+                        const __half2* hh = reinterpret_cast<const __half2*>(&resh[u]);
+                        const __half2* ll = reinterpret_cast<const __half2*>(&resl[u]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            res[2 * j] = xh_join(__low2half(hh[j]), __low2half(ll[j]));
+                            res[2 * j + 1] = xh_join(__high2half(hh[j]), __high2half(ll[j]));
+                        }
+                    } else {
+                        res[0] = __uint_as_float(resh[u].x); res[1] = __uint_as_float(resh[u].y);
+                        res[2] = __uint_as_float(resh[u].z); res[3] = __uint_as_float(resh[u].w);
+                        res[4] = __uint_as_float(resl[u].x); res[5] = __uint_as_float(resl[u].y);
+                        res[6] = __uint_as_float(resl[u].z); res[7] = __uint_as_float(resl[u].w);
+                    }
+                    float sc[8], sh[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; }
+                    if (a.scale) {
+                        const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.scale + col));
+                        const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.scale + col + 4));
+                        sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+                    }
+                    if (a.shift) {
+                        const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.shift + col));
+                        const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.shift + col + 4));
+                        sh[0] = s0.x; sh[1] = s0.y; sh[2] = s0.z; sh[3] = s0.w; sh[4] = s1.x; sh[5] = s1.y; sh[6] = s1.z; sh[7] = s1.w;
+                    }
+                    float ss = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float v = __fmul_rn(y[j], a.acc_scale);              // exact: power of two
+                        v = a.scale ? __fmaf_rn(v, sc[j], sh[j]) : __fadd_rn(v, sh[j]);
+                        if (a.residual) v = __fadd_rn(v, res[j]);
+                        if (a.relu) v = fmaxf(v, 0.f);
+                        y[j] = v;
+                        ss = __fmaf_rn(v, v, ss);
+                    }
+                    if (a.l2norm) {              // host guarantees the whole row sits in this CTA (cout <= 128): c8n lanes per row
+                        for (int o = 1; o < c8n; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                        const float nrm = sqrtf(ss);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) y[j] = __fdiv_rn(y[j], nrm);
+                    }
+                    if (rowv[u] >= 0) {
+                        uint8_t* orow_p = a.out + (size_t)rowv[u] * row_bytes;
+                        if (a.out_packed) xh_store8(orow_p, col, y);
+                        else {
+                            *reinterpret_cast<float4*>(orow_p + (size_t)col * 4) = make_float4(y[0], y[1], y[2], y[3]);
+                            *reinterpret_cast<float4*>(orow_p + (size_t)col * 4 + 16) = make_float4(y[4], y[5], y[6], y[7]);
+                        }
+                    }
+                }
+            }
+            bar_sync_producers();                // the buffers are reused by the next tile
+        }
+        tc_fence_before();
+        if (timing) g_times[blockIdx.x][4] = clock64();
+    } else if (warp == wload_warp) {
+        // =========================================================== weight slabs: one TMA bulk copy each
+        if (lane == 0) {
+            uint32_t w_it = 0;
+            for (int i = 0; i < nitems; ++i) {
+                const uint32_t it = items[i];
+                if (!item_first(it)) continue;
+                const uint32_t ws = w_it % NSW;
+                mbar_wait(w_empty + 8 * ws, ((w_it / NSW) & 1u) ^ 1u);
+                if (ablate & 4) { mbar_arrive(w_full + 8 * ws); ++w_it; continue; }
+                mbar_expect_tx(w_full + 8 * ws, W_BYTES);
+                bulk_g2s(sW + ws * W_BYTES,
+                         a.wt_img + (((size_t)item_k(it) * nch + item_c(it)) * nparts + part) * (W_BYTES / 2), W_BYTES,
+                         w_full + 8 * ws);
+                ++w_it;
+            }
+        }
+        __syncwarp();
+    } else {
+        // =========================================================== MMA issuers
+        // One tcgen05.mma costs its issuing thread ~110 cycles - about what the tensor pipe needs to execute it at N = 256 -
+        // and every barrier wait another ~250, during which a single issuer leaves the pipe idle.  PER_TILE: each of the
+        // CTA's two tiles has its own issuing warp; thread t walks the whole item list, takes the items of tile t (in list
+        // order: the accumulation order of a row stays fixed, results are deterministic) and the two threads' bookkeeping
+        // overlaps the other one's MMAs.  A weight slab is released when every issuing thread is past it (a commit from a
+        // thread that used the slab, a plain arrival from one that did not).
+        const int t_own = warp - mma_warp;
+        if (lane == 0 && t_own < NMMA) {
+            uint32_t w_it = 0, started = 0, ws = 0;
+            bool used = false;
+            uint32_t it = nitems > 0 ? items[0] : 0u;
+            for (int i = 0; i < nitems; ++i) {
+                const uint32_t it_next = i + 1 < nitems ? items[i + 1] : (1u << 12);
+                if (item_first(it)) {
+                    // waited for even when this tile skips the slab: it orders this thread's arrival on the slab's "empty"
+                    // barrier after the completion of that barrier's previous phase
+                    ws = w_it % NSW;
+                    used = false;
+                    mbar_wait(w_full + 8 * ws, (w_it / NSW) & 1u);
+                }
+                const int t = item_t(it);
+                if (!PER_TILE || t == t_own) {
+                    used = true;
+                    const uint32_t wh = sW + ws * W_BYTES;
+                    const uint32_t s = item_stage(it);
+                    const uint32_t d = tmem_base + (uint32_t)(t * TR);
+                    if (tracing && i < 96) g_trace[tcta][i][3] = clock64();
+                    mbar_wait(a_full + 8 * s, item_parity(it));
+                    if (tracing && i < 96) g_trace[tcta][i][4] = clock64();
+                    fence_proxy_async();                 // the stage was written through the generic proxy (cp.async)
+                    tc_fence_after();
+                    const uint32_t xs = sX + s * XS_BYTES;
+                    uint32_t acc = (started >> t) & 1u;
+                    if (!(ablate & 1)) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {                        // virtual channels: j = 0, 1 x_hi; j = 2, 3 x_lo'
+                            umma_f16(d, make_desc_sw128(wh + j * 32), make_desc_sw128(xs + j * 32), IDESC, acc);
+                            acc = 1u;
+                        }
+                        if (WIDE) {
+#pragma unroll
+                            for (int j = 0; j < 2; ++j)                      // W_lo x_hi
+                                umma_f16(d, make_desc_sw128(wh + 128 * 128 + j * 32), make_desc_sw128(xs + j * 32), IDESC, 1u);
+                        }
+                    }
+                    umma_commit(a_empty + 8 * s);
+                    started |= 1u << t;
+                    if (tracing && i < 96) g_trace[tcta][i][5] = clock64();
+                }
+                if (item_first(it_next)) {               // past this slab
+                    if (used) umma_commit(w_empty + 8 * ws);
+                    else mbar_arrive(w_empty + 8 * ws);
+                    ++w_it;
+                }
+                it = it_next;
+            }
+            umma_commit(done_bar);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == mma_warp) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// weight [K, cin, cout] fp32 -> shared-memory images of w' = w * wscale (a power of two).  Per (k, 32-channel chunk ci,
+// 128-channel part p) one slab of 2 * RP rows x 64 virtual channels (RP = 64 when cout <= 64, else 128):
+//   rows [0, RP)     : [ W_hi(32 channels) | W_hi * 2^-11 ]      W_hi = fp16(w')
+//   rows [RP, 2 RP)  : [ W_lo(32 channels) | W_lo * 2^-11 ]      W_lo = fp16(w' - W_hi)   (second half unread when RP = 128)
+// row n = output channel p*128 + n (zero rows when n >= cout); each row's eight 16-byte chunks XOR-swizzled with
+// (row & 7) exactly as the SWIZZLE_128B K-major UMMA descriptor expects them.
+__global__ void split_weights_h_kernel(const float* __restrict__ w, int K, int cin, int cout, float wscale, __half* __restrict__ img) {
+    const int RP = cout <= 64 ? 64 : 128;
+    const int nparts = cout <= 64 ? 1 : cout / 128;
+    const size_t total = (size_t)K * (cin / KC) * nparts * RP * KC;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int cl = (int)(i % KC);
+    const int n = (int)((i / KC) % RP);
+    const int p = (int)((i / ((size_t)KC * RP)) % nparts);
+    const int ci = (int)((i / ((size_t)KC * RP * nparts)) % (cin / KC));
+    const int k = (int)(i / ((size_t)KC * RP * nparts * (cin / KC)));
+    const int ch = p * 128 + n;
+    __half h = __float2half_rn(0.f), l = h, h2 = h, l2 = h;
+    if (ch < cout) {
+        const float x = __fmul_rn(w[((size_t)k * cin + ci * KC + cl) * cout + ch], wscale);
+        h = __float2half_rn(x);
+        l = __float2half_rn(__fsub_rn(x, __half2float(h)));
+        h2 = __float2half_rn(__fmul_rn(__half2float(h), LO_INV));
+        l2 = __float2half_rn(__fmul_rn(__half2float(l), LO_INV));
+    }
+    const size_t slab = (((size_t)k * (cin / KC) + ci) * nparts + p) * (2 * (size_t)RP * 64);
+    // virtual channel v of row r sits at r * 64 + (((v >> 3) ^ (r & 7)) << 3 | (v & 7))   (halves)
+    const int v0 = cl, v1 = cl + 32;
+    const size_t rh = slab + (size_t)n * 64, rl = slab + (size_t)(RP + n) * 64;
+    const int sw = n & 7;                                          // (RP + n) & 7 == n & 7
+    img[rh + ((((v0 >> 3) ^ sw) << 3) | (v0 & 7))] = h;
+    img[rh + ((((v1 >> 3) ^ sw) << 3) | (v1 & 7))] = h2;
+    img[rl + ((((v0 >> 3) ^ sw) << 3) | (v0 & 7))] = l;
+    img[rl + ((((v1 >> 3) ^ sw) << 3) | (v1 & 7))] = l2;
+}
+
+// fp32 [n, c] <-> split-half rows; one thread per 8 channels
+__global__ void xh_pack_kernel(const float* __restrict__ x, long long n8, int c, uint8_t* __restrict__ xh) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    const int c8n = c >> 3;
+    const long long r = i / c8n;
+    const int col = (int)(i - r * c8n) * 8;
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(x + r * c + col));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(x + r * c + col + 4));
+    const float y[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    xh_store8(xh + (size_t)r * c * 4, col, y);
+}
+__global__ void xh_unpack_kernel(const uint8_t* __restrict__ xh, long long n8, int c, float* __restrict__ x) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    const int c8n = c >> 3;
+    const long long r = i / c8n;
+    const int col = (int)(i - r * c8n) * 8;
+    float y[8];
+    xh_load8(xh + (size_t)r * c * 4, col, y);
+    *reinterpret_cast<float4*>(x + r * c + col) = make_float4(y[0], y[1], y[2], y[3]);
+    *reinterpret_cast<float4*>(x + r * c + col + 4) = make_float4(y[4], y[5], y[6], y[7]);
+}
+
+// masks[t] = OR over the 256 columns of tile t of the bit mask "offset k has a neighbour"
+__global__ void tile_masks_kernel(const int* __restrict__ nbr, int K, int n_out, uint32_t* __restrict__ masks) {
+    __shared__ uint32_t m_s;
+    if (threadIdx.x == 0) m_s = 0;
+    __syncthreads();
+    const int col = blockIdx.x * TR + threadIdx.x;
+    uint32_t m = 0;
+    if (col < n_out) {
+        int v[27];
+#pragma unroll
+        for (int k = 0; k < 27; ++k) v[k] = k < K ? __ldg(nbr + (size_t)k * n_out + col) : -1;
+#pragma unroll
+        for (int k = 0; k < 27; ++k) m |= (uint32_t)(v[k] >= 0) << k;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+    if ((threadIdx.x & 31) == 0 && m) atomicOr(&m_s, m);
+    __syncthreads();
+    if (threadIdx.x == 0) masks[blockIdx.x] = m_s;
+}
+
+template <bool WIDE, int NSW, int NXS>
+int launch_h(const HArgs& a, cudaStream_t stream) {
+    const size_t smem = (size_t)NXS * XS_BYTES + (size_t)NSW * (WIDE ? 256 : 128) * 128;
+    EYOC_CUDA(cudaFuncSetAttribute(sparse_conv_h_kernel<WIDE, NSW, NXS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles = (a.n_out + TR - 1) / TR;
+    dim3 grid((tiles + NTILE - 1) / NTILE, WIDE ? a.cout / 128 : 1);
+    sparse_conv_h_kernel<WIDE, NSW, NXS><<<grid, NPT + 96, smem, stream>>>(a);
+    EYOC_LAUNCH_CHECK();
+    return EYOC_OK;
+}
+
+}  // namespace
+
+extern "C" int eyoc_debug_convh_ablate(int flags) {
+    EYOC_CUDA(cudaMemcpyToSymbol(g_ablate, &flags, sizeof(int)));
+    return EYOC_OK;
+}
+
+extern "C" int eyoc_debug_convh_times(long long* host_out_1024x6) {
+    EYOC_CUDA(cudaMemcpyFromSymbol(host_out_1024x6, g_times, sizeof(long long) * 1024 * 6));
+    return EYOC_OK;
+}
+
+extern "C" int eyoc_debug_convh_trace(long long* host_out_4x96x6) {
+    EYOC_CUDA(cudaMemcpyFromSymbol(host_out_4x96x6, g_trace, sizeof(long long) * 4 * 96 * 6));
+    return EYOC_OK;
+}
+
+extern "C" size_t eyoc_convh_weight_image_halves(int K, int cin, int cout) {
+    const size_t RP = cout <= 64 ? 64 : 128, nparts = cout <= 64 ? 1 : cout / 128;
+    return (size_t)K * (cin / KC) * nparts * 2 * RP * 64;
+}
+
+extern "C" int eyoc_convh_split_weights(const float* weight, int K, int cin, int cout, float wscale, void* wt_img, cudaStream_t stream) {
+    EYOC_CHECK_ARG(weight && wt_img && K >= 1 && cin >= 1 && cout >= 1, "eyoc_convh_split_weights: bad argument");
+    EYOC_CHECK_ARG(cin % KC == 0 && (cout == 32 || cout == 64 || cout == 128 || cout == 256),
+                   "eyoc_convh_split_weights: cin must be a multiple of 32 and cout one of 32, 64, 128, 256");
+    int e = 0;
+    EYOC_CHECK_ARG(wscale > 0.f && frexpf(wscale, &e) == 0.5f, "eyoc_convh_split_weights: wscale must be a power of two");
+    const size_t total = eyoc_convh_weight_image_halves(K, cin, cout) / 4;
+    split_weights_h_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(weight, K, cin, cout, wscale, (__half*)wt_img);
+    EYOC_LAUNCH_CHECK();
+    return EYOC_OK;
+}
+
+extern "C" int eyoc_xh_pack(const float* x, int64_t n, int c, void* xh, cudaStream_t stream) {
+    EYOC_CHECK_ARG(x && xh && n >= 0 && c >= 32 && c % 32 == 0, "eyoc_xh_pack: bad argument (c must be a multiple of 32)");
+    if (n == 0) return EYOC_OK;
+    const long long n8 = (long long)n * (c / 8);
+    xh_pack_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>(x, n8, c, (uint8_t*)xh);
+    EYOC_LAUNCH_CHECK();
+    return EYOC_OK;
+}
+
+extern "C" int eyoc_xh_unpack(const void* xh, int64_t n, int c, float* x, cudaStream_t stream) {
+    EYOC_CHECK_ARG(x && xh && n >= 0 && c >= 32 && c % 32 == 0, "eyoc_xh_unpack: bad argument (c must be a multiple of 32)");
+    if (n == 0) return EYOC_OK;
+    const long long n8 = (long long)n * (c / 8);
+    xh_unpack_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>((const uint8_t*)xh, n8, c, x);
+    EYOC_LAUNCH_CHECK();
+    return EYOC_OK;
+}
+
+extern "C" int eyoc_tile_masks(const int32_t* nbr_tiled, int K, int64_t n_out, uint32_t* masks, cudaStream_t stream) {
+    EYOC_CHECK_ARG(nbr_tiled && masks && K >= 1 && K <= 27 && n_out >= 0 && n_out < (1ll << 31), "eyoc_tile_masks: bad argument");
+    if (n_out == 0) return EYOC_OK;
+    tile_masks_kernel<<<(unsigned)((n_out + TR - 1) / TR), TR, 0, stream>>>(nbr_tiled, K, (int)n_out, masks);
+    EYOC_LAUNCH_CHECK();
+    return EYOC_OK;
+}
+
+extern "C" int eyoc_sparse_conv_h_supported(int c0, int c1, int cout, int K, int l2norm) {
+    const int cin = c0 + c1;
+    if (cin % KC || c0 % KC || K < 1 || K > 27 || cin / KC > 12) return 0;
+    if (!(cout == 32 || cout == 64 || cout == 128 || cout == 256)) return 0;
+    if (l2norm && cout > 128) return 0;
+    return 1;
+}
+
+extern "C" int eyoc_sparse_conv_h(const void* in0, int c0, const void* in1, int c1, const int32_t* nbr, int K, int64_t n_out,
+                                  const int32_t* row_perm, int nbr_tiled, const uint32_t* tile_masks, const void* wt_img,
+                                  float acc_scale, const float* scale, const float* shift, const void* residual,
+                                  int residual_packed, int relu, int l2norm, void* out, int out_packed, int cout,
+                                  cudaStream_t stream) {
+    EYOC_CHECK_ARG(in0 && wt_img && out, "eyoc_sparse_conv_h: null argument");
+    EYOC_CHECK_ARG((in1 != nullptr) == (c1 > 0), "eyoc_sparse_conv_h: in1 and c1 must be given together");
+    EYOC_CHECK_ARG(nbr || K == 1, "eyoc_sparse_conv_h: a neighbour table is required when K > 1");
+    EYOC_CHECK_ARG(eyoc_sparse_conv_h_supported(c0, c1, cout, K, l2norm), "eyoc_sparse_conv_h: unsupported shape c0=%d c1=%d cout=%d K=%d", c0, c1, cout, K);
+    EYOC_CHECK_ARG(n_out >= 0 && n_out < (1ll << 31), "eyoc_sparse_conv_h: bad n_out");
+    EYOC_CHECK_ARG(!nbr_tiled || row_perm, "eyoc_sparse_conv_h: a tiled neighbour table needs row_perm");
+    EYOC_CHECK_ARG(!tile_masks || nbr_tiled, "eyoc_sparse_conv_h: tile masks describe a tiled neighbour table");
+    EYOC_CHECK_ARG(acc_scale > 0.f, "eyoc_sparse_conv_h: acc_scale must be positive");
+    EYOC_CHECK_ARG(!(l2norm && out_packed), "eyoc_sparse_conv_h: the normalised output is fp32");
+    if (n_out == 0) return EYOC_OK;
+    HArgs a{(const uint8_t*)in0, c0, (const uint8_t*)in1, c1, nbr, row_perm, tile_masks, (const __half*)wt_img, scale, shift,
+            (const uint8_t*)residual, residual_packed, (uint8_t*)out, out_packed, acc_scale, K, (int)n_out, cout, relu, l2norm,
+            nbr_tiled};
+    if (cout <= 64) return launch_h<false, 2, 6>(a, stream);       // 6 x 32 KB X stages + 2 x 16 KB weight slabs
+    return launch_h<true, 2, 5>(a, stream);                          // 5 x 32 KB X stages + 2 x 32 KB weight slabs
+}

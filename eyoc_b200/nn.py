@@ -41,6 +41,16 @@ class MinkowskiConvolution(nn.Module):
             cache = self._tc_image = (ver, split_weights(k.detach()))
         return cache[1]
 
+    def h_image(self):
+        """(wt_img, acc_scale) of the fp16 hi/lo path, cached per parameter version: the weights are pre-scaled by a power
+        of two so that max |w'| lies in [2^13, 2^14) (fp16 range with 2^-11-scaled copies still normal), acc_scale undoes it."""
+        k = self.kernel
+        ver = (int(k._version), k.data_ptr(), k.device)
+        cache = getattr(self, '_h_image', None)
+        if cache is None or cache[0] != ver:
+            cache = self._h_image = (ver, split_weights_h(k.detach()))
+        return cache[1]
+
     def reset_parameters(self):
         with torch.no_grad():
             n = self.in_channels * self.kernel_size ** 3
@@ -100,9 +110,11 @@ class MinkowskiBatchNorm(nn.Module):
 
 
 # Data path of the convolutions that qualify (C_in multiple of 32, C_out in {32,64,128,256}, K <= 27):
-#   'tf32x3' : tcgen05 tensor cores, 3-term TF32 split, fp32 accumulation in TMEM (csrc/sparse_conv_tc.cu)
+#   'f16x3'  : tcgen05 tensor cores, fp16 hi/lo split of both operands (22 significant bits each, exact products, fp32
+#              accumulation in TMEM), activations kept in HBM in the split-half format (csrc/sparse_conv_h.cu)
+#   'tf32x3' : tcgen05 tensor cores, 3-term TF32 split, fp32 activations (csrc/sparse_conv_tc.cu)
 #   'fp32'   : fp32 FMA register-tile kernel (csrc/sparse_conv.cu); also the path of everything that does not qualify
-CONV_MODE = 'tf32x3'
+CONV_MODE = 'f16x3'
 # Tensor-core convolutions tile their output rows in (cloud group, neighbour pattern) order (CoordinateManager.tiled_map)
 TILE_ORDER = True
 
@@ -118,6 +130,58 @@ def split_weights(weight):
         _C.check(_C.lib().eyoc_conv_split_weights(_C.ptr(w3.contiguous()), _C.c_int(K), _C.c_int(cin), _C.c_int(cout),
                                                   _C.ptr(img), _C.stream()))
     return img
+
+
+def split_weights_h(weight):
+    """[K, cin, cout] (or [cin, cout]) -> (wt_img fp16, acc_scale): the split / swizzled weight image of the fp16 path."""
+    w3 = weight if weight.dim() == 3 else weight[None]
+    K, cin, cout = w3.shape
+    amax = float(w3.abs().max().item()) if w3.numel() else 0.0
+    e = math.frexp(amax)[1] if amax > 0 and math.isfinite(amax) else 14      # amax = m * 2^e, m in [0.5, 1)
+    a = max(-100, min(100, 14 - e))
+    wscale = 2.0 ** a
+    n = _C.lib().eyoc_convh_weight_image_halves(_C.c_int(K), _C.c_int(cin), _C.c_int(cout))
+    img = torch.empty(n, dtype=torch.float16, device=weight.device)
+    with torch.cuda.device(weight.device):
+        _C.check(_C.lib().eyoc_convh_split_weights(_C.ptr(w3.contiguous()), _C.c_int(K), _C.c_int(cin), _C.c_int(cout),
+                                                   _C.c_float(wscale), _C.ptr(img), _C.stream()))
+    return img, 2.0 ** -a
+
+
+def h_supported(c0, c1, cout, K, l2norm):
+    return CONV_MODE == 'f16x3' and bool(_C.lib().eyoc_sparse_conv_h_supported(c0, c1, cout, K, int(l2norm)))
+
+
+def sparse_conv_h_raw(in0, in1, nbr, weight, scale, shift, residual, relu, l2norm, out, row_perm=None, nbr_tiled=False,
+                      tile_masks=None, h_img=None):
+    """Thin call into eyoc_sparse_conv_h.  in0 / in1 split-half [n, 2 c] fp16; residual and out are split-half when
+    their dtype is fp16, fp32 rows otherwise; h_img = cached ``split_weights_h(weight)``."""
+    _C.require_cuda(in0, in1, nbr, weight, scale, shift, residual, out, row_perm, tile_masks)
+    if in0.dtype != torch.float16 or (in1 is not None and in1.dtype != torch.float16):
+        raise RuntimeError('eyoc_sparse_conv_h takes split-half (fp16) inputs: see sparse.xh_pack')
+    c0 = in0.shape[1] // 2
+    c1 = in1.shape[1] // 2 if in1 is not None else 0
+    K = 1 if weight.dim() == 2 else weight.shape[0]
+    cout = weight.shape[-1]
+    if weight.shape[-2] != c0 + c1:
+        raise RuntimeError(f'kernel expects {weight.shape[-2]} input channels, got {c0}+{c1}')
+    img, acc_scale = h_img if h_img is not None else split_weights_h(weight)
+    ev = None
+    if PROFILE is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    with torch.cuda.device(in0.device):
+        _C.check(_C.lib().eyoc_sparse_conv_h(
+            _C.ptr(in0), _C.c_int(c0), _C.ptr(in1), _C.c_int(c1), _C.ptr(nbr), _C.c_int(K), _C.c_int64(out.shape[0]),
+            _C.ptr(row_perm), _C.c_int(int(nbr_tiled)), _C.ptr(tile_masks), _C.ptr(img), _C.c_float(acc_scale), _C.ptr(scale),
+            _C.ptr(shift), _C.ptr(residual), _C.c_int(int(residual is not None and residual.dtype == torch.float16)),
+            _C.c_int(int(relu)), _C.c_int(int(l2norm)), _C.ptr(out), _C.c_int(int(out.dtype == torch.float16)), _C.c_int(cout),
+            _C.stream()))
+    if ev is not None:
+        ev[1].record()
+        PROFILE.append((ev[0], ev[1], dict(K=K, cin=c0 + c1, cout=cout, n_out=out.shape[0], nbr=nbr,
+                                           residual=residual is not None)))
+    return out
 
 
 # When set to a list, every sparse_conv_raw call appends (start_event, end_event, meta) - bench.py uses it to time
@@ -177,18 +241,26 @@ def _sparse_conv_call(in0, in1, nbr, weight, scale, shift, residual, relu, l2nor
 def conv_bn_act(x, conv, norm=None, residual=None, relu=False, l2norm=False, skip=None):
     """One fused launch: conv (+ fused concat with ``skip``) -> BN affine / bias -> + residual -> ReLU -> L2 norm.
 
-    x, skip, residual are SparseTensors; returns a SparseTensor on the output coordinate map."""
+    x, skip, residual are SparseTensors; returns a SparseTensor on the output coordinate map.  In 'f16x3' mode the
+    convolutions that qualify read and write split-half features (SparseTensor.Fh); ``.F`` of the result converts on
+    first access, the normalised network output is written as fp32 directly."""
     mgr = x.coordinate_manager
     ts_in = x.coordinate_map_key.tensor_stride
     ts_out = conv.out_stride(ts_in)
+    c0_, c1_ = x.num_channels, (skip.num_channels if skip is not None else 0)
+    K = conv.kernel_size ** 3
+    use_h = h_supported(c0_, c1_, conv.out_channels, K, l2norm)
+    use_tc = use_h or tc_supported(c0_, c1_, conv.out_channels, K, l2norm)
     nbr = None
     row_perm = None
+    masks = None
     tiled = False
     if conv.kernel_size > 1 or ts_out != ts_in:
-        c0_, c1_ = x.F.shape[1], (skip.F.shape[1] if skip is not None else 0)
-        if TILE_ORDER and tc_supported(c0_, c1_, conv.out_channels, conv.kernel_size ** 3, l2norm):
+        if TILE_ORDER and use_tc:
             nbr, row_perm = mgr.tiled_map(ts_in, ts_out, conv.kernel_size, transposed=conv.TRANSPOSED)
             tiled = True
+            if use_h:
+                masks = mgr.tile_masks(ts_in, ts_out, conv.kernel_size, transposed=conv.TRANSPOSED)
         else:
             nbr = mgr.kernel_map(ts_in, ts_out, conv.kernel_size, transposed=conv.TRANSPOSED)
             if conv.TRANSPOSED:
@@ -202,16 +274,25 @@ def conv_bn_act(x, conv, norm=None, residual=None, relu=False, l2norm=False, ski
             shift = shift + conv.bias.view(-1) * scale
     elif conv.bias is not None:
         shift = conv.bias.view(-1)
+    key = CoordinateMapKey(ts_out)
+    if use_h:
+        dev = x.device
+        out = torch.empty((n_out, conv.out_channels) if l2norm else (n_out, 2 * conv.out_channels),
+                          dtype=torch.float32 if l2norm else torch.float16, device=dev)
+        sparse_conv_h_raw(x.Fh, skip.Fh if skip is not None else None, nbr, conv.kernel.detach(), scale, shift,
+                          residual.Fh if residual is not None else None, relu, l2norm, out, row_perm, tiled, masks,
+                          h_img=conv.h_image())
+        if l2norm:
+            return SparseTensor(out, coordinate_map_key=key, coordinate_manager=mgr)
+        return SparseTensor(features_xh=out, coordinate_map_key=key, coordinate_manager=mgr)
     in0 = x.F if x.F.is_contiguous() else x.F.contiguous()
     in1 = None
     if skip is not None:
         in1 = skip.F if skip.F.is_contiguous() else skip.F.contiguous()
     out = torch.empty((n_out, conv.out_channels), dtype=torch.float32, device=in0.device)
     sparse_conv_raw(in0, in1, nbr, conv.kernel.detach(), scale, shift, residual.F if residual is not None else None, relu,
-                    l2norm, out, row_perm, tiled,
-                    wt_img=conv.tc_image() if tc_supported(in0.shape[1], in1.shape[1] if in1 is not None else 0,
-                                                            conv.out_channels, conv.kernel_size ** 3, l2norm) else None)
-    return SparseTensor(out, coordinate_map_key=CoordinateMapKey(ts_out), coordinate_manager=mgr)
+                    l2norm, out, row_perm, tiled, wt_img=conv.tc_image() if use_tc else None)
+    return SparseTensor(out, coordinate_map_key=key, coordinate_manager=mgr)
 
 
 def cat(*tensors):

@@ -58,6 +58,7 @@ class CoordinateManager:
         self.levels = {}
         self._maps = {}
         self._tiled = {}
+        self._tile_masks = {}
         self._perms = {}
         self.max_batch = 0
         self._status = torch.zeros(2, dtype=torch.int32, device=self.device)
@@ -168,6 +169,19 @@ class CoordinateManager:
             self._tiled[key] = (tiled, perm)
         return self._tiled[key]
 
+    def tile_masks(self, ts_in, ts_out, ksize, transposed=False):
+        """Per 256-row tile of ``tiled_map`` the bit mask of kernel offsets that have a neighbour (eyoc_tile_masks):
+        computed once per map instead of by every CTA of every convolution that uses it."""
+        key = (ts_in, ts_out, ksize, transposed)
+        if key not in self._tile_masks:
+            tiled, _ = self.tiled_map(ts_in, ts_out, ksize, transposed)
+            K, n_out = tiled.shape
+            masks = torch.empty(max(1, (n_out + 255) // 256), dtype=torch.int32, device=self.device)
+            with torch.cuda.device(self.device):
+                _C.check(_C.lib().eyoc_tile_masks(_C.ptr(tiled), _C.c_int(K), _C.c_int64(n_out), _C.ptr(masks), _C.stream()))
+            self._tile_masks[key] = masks
+        return self._tile_masks[key]
+
     def parity_perm(self, ts):
         """Row order of level ``ts`` grouped by parity class (CTA-uniform offsets for transposed convs)."""
         if ts not in self._perms:
@@ -180,32 +194,75 @@ class CoordinateManager:
         return self._perms[ts]
 
 
-class SparseTensor:
-    """Features [N, C] fp32 on a coordinate set; row order == input order (the reference relies on it)."""
+def xh_pack(x):
+    """fp32 [n, c] (c % 32 == 0) -> split-half rows [n, 2 c] fp16 (eyoc_xh_pack)."""
+    _C.require_cuda(x)
+    x = x.to(torch.float32).contiguous()
+    n, c = x.shape
+    out = torch.empty((n, 2 * c), dtype=torch.float16, device=x.device)
+    with torch.cuda.device(x.device):
+        _C.check(_C.lib().eyoc_xh_pack(_C.ptr(x), _C.c_int64(n), _C.c_int(c), _C.ptr(out), _C.stream()))
+    return out
 
-    def __init__(self, features, coordinates=None, coordinate_map_key=None, coordinate_manager=None, device=None,
-                 tensor_stride=1):
-        if device is not None:
+
+def xh_unpack(xh):
+    """split-half rows [n, 2 c] fp16 -> fp32 [n, c] (eyoc_xh_unpack)."""
+    _C.require_cuda(xh)
+    n, c = xh.shape[0], xh.shape[1] // 2
+    out = torch.empty((n, c), dtype=torch.float32, device=xh.device)
+    with torch.cuda.device(xh.device):
+        _C.check(_C.lib().eyoc_xh_unpack(_C.ptr(xh.contiguous()), _C.c_int64(n), _C.c_int(c), _C.ptr(out), _C.stream()))
+    return out
+
+
+class SparseTensor:
+    """Features [N, C] fp32 on a coordinate set; row order == input order (the reference relies on it).
+
+    Inside the network the features may exist only in the SPLIT-HALF format of the fp16 tensor-core convolutions
+    (``features_xh`` [N, 2 C] fp16: per 32-channel chunk 32 hi | 32 lo' halves, include/eyoc_b200.h); ``.F`` then
+    converts once, on first access, and caches the fp32 tensor."""
+
+    def __init__(self, features=None, coordinates=None, coordinate_map_key=None, coordinate_manager=None, device=None,
+                 tensor_stride=1, features_xh=None):
+        if features is None and features_xh is None:
+            raise RuntimeError('SparseTensor needs features')
+        if device is not None and features is not None:
             features = features.to(device)
             coordinates = coordinates.to(device) if coordinates is not None else None
-        _C.require_cuda(features)
+        _C.require_cuda(features, features_xh)
+        dev = features.device if features is not None else features_xh.device
         if coordinate_manager is None:
             if coordinates is None:
                 raise RuntimeError('SparseTensor needs coordinates or a coordinate_manager')
-            coordinate_manager = CoordinateManager(coordinates.to(features.device))
+            coordinate_manager = CoordinateManager(coordinates.to(dev))
             coordinate_map_key = CoordinateMapKey(tensor_stride)
         elif coordinate_map_key is None:
             coordinate_map_key = CoordinateMapKey(tensor_stride)
         self._F = features
+        self._Fh = features_xh
         self.coordinate_manager = coordinate_manager
         self.coordinate_map_key = coordinate_map_key
         n = coordinate_manager.levels[coordinate_map_key.tensor_stride].coords.shape[0]
-        if features.shape[0] != n:
-            raise RuntimeError(f'features have {features.shape[0]} rows, coordinates {n}')
+        rows = features.shape[0] if features is not None else features_xh.shape[0]
+        if rows != n:
+            raise RuntimeError(f'features have {rows} rows, coordinates {n}')
 
     @property
     def F(self):
+        if self._F is None:
+            self._F = xh_unpack(self._Fh)
         return self._F
+
+    @property
+    def Fh(self):
+        """Split-half image of the features (packed on first access; needs C % 32 == 0)."""
+        if self._Fh is None:
+            self._Fh = xh_pack(self._F)
+        return self._Fh
+
+    @property
+    def num_channels(self):
+        return self._F.shape[1] if self._F is not None else self._Fh.shape[1] // 2
 
     @property
     def C(self):
@@ -217,27 +274,27 @@ class SparseTensor:
 
     @property
     def features(self):
-        return self._F
+        return self.F
 
     @property
     def device(self):
-        return self._F.device
+        return self._F.device if self._F is not None else self._Fh.device
 
     @property
     def tensor_stride(self):
         return self.coordinate_map_key.get_tensor_stride()
 
     def __len__(self):
-        return self._F.shape[0]
+        return self._F.shape[0] if self._F is not None else self._Fh.shape[0]
 
     @property
     def shape(self):
-        return self._F.shape
+        return torch.Size((len(self), self.num_channels))
 
     @property
     def decomposed_coordinates_and_features(self):
         """Per-batch-index lists (lib/trainer.py:1289)."""
-        C, F = self.C, self._F
+        C, F = self.C, self.F
         nb = int(C[:, 0].max().item()) + 1 if len(C) else 0
         coords, feats = [], []
         for b in range(nb):
@@ -271,6 +328,37 @@ def sparse_quantize(coordinates, features=None, return_index=False, quantization
         idx = torch.from_numpy(sel) if is_torch else sel
         return (out, idx) if features is None else (out, features[sel], idx)
     return out if features is None else (out, features[sel])
+
+
+def voxelize_gpu(xyz, voxel_size, cloud=None):
+    """Device-side voxelisation + collate of raw points (the step in front of the hot path, lib/data_loaders.py:936-979
+    + :31-85): returns (coords int32 [m, 4] (batch, x, y, z), sel int64 [m]) with ``coords = floor(xyz[sel] / voxel_size)``
+    and ``sel`` = first occurrence of every occupied voxel per cloud, ascending - what
+    ``ME.utils.sparse_quantize(xyz / voxel_size, return_index=True)`` selects.  xyz [n, 3] CUDA fp32; cloud [n] int32
+    batch index per point (None = one cloud)."""
+    _C.require_cuda(xyz, cloud)
+    xyz = xyz.to(torch.float32).contiguous()
+    n = xyz.shape[0]
+    dev = xyz.device
+    if cloud is not None:
+        cloud = cloud.to(torch.int32).contiguous()
+    cap = _pow2_at_least(2 * max(n, 1))
+    keys = torch.empty(cap, dtype=torch.int64, device=dev)
+    vals = torch.empty(cap, dtype=torch.int32, device=dev)
+    coords = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    sel = torch.empty(n, dtype=torch.int32, device=dev)
+    n_out = torch.zeros(1, dtype=torch.int32, device=dev)
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    lib = _C.lib()
+    ws = torch.empty(max(lib.eyoc_voxelize_workspace_bytes(_C.c_int64(n)), 8), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _C.check(lib.eyoc_voxelize(_C.ptr(xyz), _C.ptr(cloud), _C.c_int64(n), _C.c_float(float(voxel_size)), _C.ptr(keys),
+                                   _C.ptr(vals), _C.c_int64(cap), _C.ptr(coords), _C.ptr(sel), _C.ptr(n_out), _C.ptr(status),
+                                   _C.ptr(ws), _C.c_size_t(ws.numel()), _C.stream()))
+    m, st = int(n_out.item()), int(status[0].item())
+    if st & 1:
+        raise RuntimeError('voxel coordinates outside the packed 16-bit range (batch 0..65535, xyz -32768..32767)')
+    return coords[:m], sel[:m].long()
 
 
 def batched_coordinates(coords, dtype=torch.int32, device=None):

@@ -105,6 +105,15 @@ size_t eyoc_downsample_workspace_bytes(int64_t n);
 int eyoc_coords_downsample(const int32_t* coords, int64_t n, int ts_out, uint64_t* table_keys, int32_t* table_vals,
                            int64_t capacity, int32_t* coords_out, int32_t* n_out, void* workspace, size_t workspace_bytes,
                            eyoc_stream_t stream);
+/* Voxelisation + collate on the device (lib/data_loaders.py:936-979, :31-85): q = floor(xyz / voxel_size) in fp32,
+ * first occurrence of every (cloud, q) kept, in ascending point order - what ME.utils.sparse_quantize(return_index=True)
+ * followed by floor(xyz[sel] / voxel).int() gives.  xyz [n, 3]; cloud [n] = batch index per point or NULL (all 0);
+ * coords_out [n, 4] / sel_out [n]: the first *n_out rows are valid; the hash table is left pointing at the new rows
+ * (it IS the stride-1 table eyoc_hash_build would make).  status as in eyoc_hash_build (bit 0 = out of range). */
+size_t eyoc_voxelize_workspace_bytes(int64_t n);
+int eyoc_voxelize(const float* xyz, const int32_t* cloud, int64_t n, float voxel_size, uint64_t* table_keys,
+                  int32_t* table_vals, int64_t capacity, int32_t* coords_out, int32_t* sel_out, int32_t* n_out,
+                  int32_t* status, void* workspace, size_t workspace_bytes, eyoc_stream_t stream);
 /* nbr[k, o] = row in the input map of (c_o + off_k * step), else -1;  k = ix + K*(iy + K*iz), off = (ix,iy,iz) - (K-1)/2.
  * step = +tensor_stride_in for a forward convolution, -tensor_stride_out for a transposed one. */
 int eyoc_kernel_map(const int32_t* out_coords, int64_t n_out, const uint64_t* in_table_keys, const int32_t* in_table_vals,
@@ -160,6 +169,32 @@ int eyoc_sparse_conv_tc(const float* in0, int c0, const float* in1, int c1, cons
                         const int32_t* row_perm, int nbr_tiled, const float* wt_img, const float* scale,
                         const float* shift, const float* residual, int relu, int l2norm, float* out, int cout,
                         eyoc_stream_t stream);
+
+/* fp16 hi/lo split data path of the same operator (csrc/sparse_conv_h.cu): tcgen05.mma kind::f16, activations kept in
+ * HBM in the SPLIT-HALF format - a row of c channels (c % 32 == 0) is c / 32 chunks of 128 bytes, each 32 fp16 "hi"
+ * values followed by 32 fp16 "lo'" values with x = hi + lo' * 2^-11 (|x| < 65504; 22 significant bits, 4 c bytes per
+ * row like fp32) - so a gathered row chunk is the tensor-core operand as it lies in memory.
+ * in0 / in1 / residual (when residual_packed) / out (when out_packed) are split-half; otherwise fp32 rows.
+ * Weights: wt_img = eyoc_convh_split_weights(weight * wscale) with wscale a power of two chosen by the caller so that
+ * max |w| * wscale lies in [2^13, 2^14); acc_scale = 1 / wscale undoes it (exactly) in the epilogue.
+ * tile_masks [ceil(n_out / 256)] (eyoc_tile_masks of the tiled table) or NULL (each CTA then derives its own).
+ * Supported shapes as reported by eyoc_sparse_conv_h_supported (those of the tf32 path). */
+size_t eyoc_convh_weight_image_halves(int K, int cin, int cout);
+int eyoc_convh_split_weights(const float* weight, int K, int cin, int cout, float wscale, void* wt_img, eyoc_stream_t stream);
+int eyoc_xh_pack(const float* x, int64_t n, int c, void* xh, eyoc_stream_t stream);
+int eyoc_xh_unpack(const void* xh, int64_t n, int c, float* x, eyoc_stream_t stream);
+int eyoc_tile_masks(const int32_t* nbr_tiled, int K, int64_t n_out, uint32_t* masks, eyoc_stream_t stream);
+int eyoc_sparse_conv_h_supported(int c0, int c1, int cout, int K, int l2norm);
+int eyoc_sparse_conv_h(const void* in0, int c0, const void* in1, int c1, const int32_t* nbr, int K, int64_t n_out,
+                       const int32_t* row_perm, int nbr_tiled, const uint32_t* tile_masks, const void* wt_img,
+                       float acc_scale, const float* scale, const float* shift, const void* residual, int residual_packed,
+                       int relu, int l2norm, void* out, int out_packed, int cout, eyoc_stream_t stream);
+/* Measurement aids of the split-half kernel, as eyoc_debug_conv_ablate / eyoc_debug_conv_times above. */
+int eyoc_debug_convh_ablate(int flags);
+int eyoc_debug_convh_times(long long* host_out_1024x6);
+/* bit 4 of the flags: CTAs 200..203 record clock64 per work item (first 96) at {producer: empty-wait start, end, arrival;
+ * MMA thread: full-wait start, end, after commit}. */
+int eyoc_debug_convh_trace(long long* host_out_4x96x6);
 
 /* ---------------------------------------------------------------- host-side index planning (no device work)
  * The six numpy draws the reference makes per pair on the global legacy RandomState (scripts/test_kitti.py:33-34,

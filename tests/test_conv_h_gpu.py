@@ -1,0 +1,161 @@
+"""GPU: fp16 hi/lo split tensor-core sparse convolution (csrc/sparse_conv_h.cu, 'f16x3') - the split-half activation
+format, the kernel shape by shape against an fp64 gather-GEMM restatement (and the fp32 FMA kernel beside it), tiled
+tables with precomputed tile masks, and the whole ResUNetBN2C forward against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from tests.test_conv_tc_gpu import _ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _restore_conv_mode():
+    from eyoc_b200 import nn as enn
+    saved = enn.CONV_MODE
+    yield
+    enn.CONV_MODE = saved
+
+
+def test_split_half_format_round_trip():
+    """x = hi + lo' 2^-11 with hi = fp16(x), lo' = fp16((x - hi) 2^11): layout [n, c/32, (hi | lo'), 32] halves,
+    22 significant bits, exact for fp16-representable values and for zeros."""
+    from eyoc_b200.sparse import xh_pack, xh_unpack
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn(1000, 96, generator=g) * torch.logspace(-4, 3, 96)[None]).cuda()
+    x[0] = 0.0
+    x[1] = torch.randn(96, generator=g).half().float().cuda()
+    xh = xh_pack(x)
+    assert xh.shape == (1000, 192) and xh.dtype == torch.float16
+    v = xh.view(1000, 3, 2, 32).float()
+    hi, lo = v[:, :, 0].reshape(1000, 96), v[:, :, 1].reshape(1000, 96)
+    assert torch.equal(hi, x.half().float())
+    assert torch.equal(lo, ((x - hi) * 2048).half().float())
+    back = xh_unpack(xh)
+    assert torch.equal(back[:2], x[:2])
+    err = (back - x).abs()[2:]
+    # 22 significant bits while lo' is a normal fp16 number, an absolute floor of 2^-36 (half a subnormal step / 2^11) below
+    assert bool((err <= x.abs()[2:] * 2.0 ** -22 + 2.0 ** -35).all()), float((err / x.abs()[2:].clamp(min=1e-30)).max())
+
+
+@pytest.mark.parametrize('c0,c1,cout,K,n_in,n_out,opts', [
+    (32, 0, 32, 27, 700, 700, dict(bn=True, relu=True)),
+    (32, 0, 64, 27, 900, 300, dict(bn=True)),
+    (64, 0, 64, 27, 1500, 1500, dict(bn=True, residual=True, relu=True)),
+    (128, 0, 128, 27, 400, 400, dict(bn=True, relu=True)),
+    (128, 0, 256, 27, 500, 150, dict(bn=True)),
+    (256, 0, 256, 27, 130, 130, dict(bn=True, residual=True, relu=True)),
+    (256, 0, 128, 27, 130, 600, dict(bn=True, perm=True)),
+    (128, 128, 64, 27, 300, 1000, dict(bn=True, perm=True)),
+    (64, 32, 64, 1, 1000, 1000, dict(relu=True)),
+    (64, 0, 32, 1, 1000, 1000, dict(bias=True, l2norm=True)),
+    (64, 0, 64, 27, 5000, 40000, dict(bn=True, relu=True)),          # many CTAs
+    (128, 256, 128, 27, 300, 700, dict(bn=True, relu=True)),         # 12 chunks (ResUNetFatBN's widest concat)
+])
+def test_h_conv_matches_fp64(c0, c1, cout, K, n_in, n_out, opts):
+    from eyoc_b200 import nn as enn
+    from eyoc_b200.sparse import xh_pack, xh_unpack
+    g = torch.Generator().manual_seed(c0 * 7 + cout + K + n_out)
+    dev = 'cuda'
+    in0 = torch.randn(n_in, c0, generator=g).to(dev)
+    in1 = torch.randn(n_in, c1, generator=g).to(dev) if c1 else None
+    cin = c0 + c1
+    W = (torch.randn((K, cin, cout) if K > 1 else (cin, cout), generator=g) / np.sqrt(cin * K)).to(dev)
+    nbr = None
+    if K > 1:
+        nbr = torch.randint(0, n_in, (K, n_out), generator=g, dtype=torch.int32)
+        nbr[torch.rand(K, n_out, generator=g) < 0.6] = -1
+        nbr[13] = torch.randint(0, n_in, (n_out,), generator=g, dtype=torch.int32)
+        nbr[5] = -1
+        nbr = nbr.to(dev)
+    scale = shift = residual = perm = None
+    if opts.get('bn'):
+        scale = (torch.rand(cout, generator=g) + 0.5).to(dev)
+        shift = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    if opts.get('bias'):
+        shift = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    if opts.get('residual'):
+        residual = torch.randn(n_out, cout, generator=g).to(dev)
+    if opts.get('perm'):
+        perm = torch.randperm(n_out, generator=g).to(torch.int32).to(dev)
+    relu, l2 = bool(opts.get('relu')), bool(opts.get('l2norm'))
+    want = _ref(in0, in1, nbr, W, scale, shift, residual, relu, l2)
+    scale_ref = float(want.abs().max())
+    h0, h1 = xh_pack(in0), (xh_pack(in1) if in1 is not None else None)
+    # fp32 output rows, fp32 residual
+    out = torch.full((n_out, cout), float('nan'), device=dev)
+    enn.sparse_conv_h_raw(h0, h1, nbr, W, scale, shift, residual, relu, l2, out, row_perm=perm)
+    torch.cuda.synchronize()
+    e = float((out.double() - want).abs().max()) / scale_ref
+    # operands carry 22 bits and the TMEM accumulation is not round-to-nearest: the error grows with the K * cin (up to
+    # 10 368) accumulated terms, as for the tf32x3 kernel (tests/test_conv_tc_gpu.py allows 5e-5)
+    tol = 1e-5 if K * cin <= 2000 else 4e-5
+    assert e < tol, e
+    if not l2:
+        # split-half output rows, split-half residual
+        outh = torch.zeros((n_out, 2 * cout), dtype=torch.float16, device=dev)
+        enn.sparse_conv_h_raw(h0, h1, nbr, W, scale, shift, xh_pack(residual) if residual is not None else None, relu, l2,
+                              outh, row_perm=perm)
+        torch.cuda.synchronize()
+        eh = float((xh_unpack(outh).double() - want).abs().max()) / scale_ref
+        assert eh < tol, eh
+
+
+def test_h_conv_tiled_masks_and_order_independence():
+    """The same rows come out whether the kernel is handed the natural table, the tiled one (each CTA deriving its tile
+    masks), or the tiled one with eyoc_tile_masks - bit for bit: the accumulation order inside a row does not depend on
+    the tile it sits in."""
+    from eyoc_b200 import nn as enn
+    from eyoc_b200.sparse import CoordinateManager, xh_pack
+    from tests.test_resunet_gpu import _cloud
+    coords = torch.from_numpy(_cloud(4000, 4, batch=6)).cuda()
+    mgr = CoordinateManager(coords)
+    nbr = mgr.kernel_map(1, 1, 3)
+    tiled, perm = mgr.tiled_map(1, 1, 3)
+    masks = mgr.tile_masks(1, 1, 3)
+    n = nbr.shape[1]
+    bits = ((tiled >= 0).long() << torch.arange(27, device='cuda')[:, None]).sum(0)
+    pad = (-n) % 256
+    want_masks = torch.cat([bits, bits.new_zeros(pad)]).view(-1, 256)
+    acc = want_masks[:, 0].clone()
+    for j in range(1, 256):
+        acc |= want_masks[:, j]
+    assert torch.equal(masks.long(), acc)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(n, 64, generator=g).cuda()
+    W = (torch.randn(27, 64, 64, generator=g) / 40).cuda()
+    xh = xh_pack(x)
+    outs = []
+    for tb, pm, flag, mk in ((nbr, None, False, None), (nbr, perm, False, None), (tiled, perm, True, None), (tiled, perm, True, masks)):
+        out = torch.full((n, 64), float('nan'), device='cuda')
+        enn.sparse_conv_h_raw(xh, None, tb, W, None, None, None, True, False, out, row_perm=pm, nbr_tiled=flag, tile_masks=mk)
+        outs.append(out)
+    want = _ref(x, None, nbr, W, None, None, None, True, False)
+    for o in outs:
+        assert float((o.double() - want).abs().max()) < 5e-6 * float(want.abs().max())
+    assert torch.equal(outs[1], outs[2]) and torch.equal(outs[2], outs[3])
+
+
+def test_forward_f16x3_vs_oracle():
+    from eyoc_b200 import nn as enn
+    from eyoc_b200.model import load_model
+    from eyoc_b200.sparse import SparseTensor
+    from oracle import resunet_oracle as RO
+    from tests.test_resunet_gpu import _cloud
+    coords = _cloud(3000, 4, batch=2)
+    feats = torch.ones((len(coords), 1), dtype=torch.float32)
+    sd = RO.make_state_dict(1, 32, 5, seed=4)
+    model = load_model('ResUNetBN2C')(1, 32, bn_momentum=0.05, normalize_feature=True, conv1_kernel_size=5, D=3)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    want = RO.resunet_forward(coords, feats, sd, True, 5)
+    assert enn.CONV_MODE == 'f16x3'                              # the shipped default
+    got = model(SparseTensor(feats.cuda(), coordinates=torch.from_numpy(coords).cuda())).F.cpu()
+    assert float((got - want).abs().max()) <= 1e-5, float((got - want).abs().max())
+    # un-normalised output: the last convolution then writes split-half rows and .F converts them
+    model.normalize_feature = False
+    raw = model(SparseTensor(feats.cuda(), coordinates=torch.from_numpy(coords).cuda()))
+    assert raw._F is None and raw._Fh is not None
+    want_raw = RO.resunet_forward(coords, feats, sd, False, 5)
+    assert float((raw.F.cpu() - want_raw).abs().max()) <= 1e-5 * max(1.0, float(want_raw.abs().max()))

@@ -112,3 +112,27 @@ def test_train_mode_rejected_and_module_api():
     assert model.state_dict()['conv1.kernel'].shape == (125, 1, 32)
     assert model.state_dict()['conv1_tr.kernel'].shape == (96, 64)
     assert model.state_dict()['final.bias'].shape == (1, 32)
+
+
+def test_voxelize_gpu_matches_reference_selection():
+    """eyoc_voxelize == sparse_quantize(xyz / 0.3, return_index=True) + floor(xyz[sel] / 0.3) (lib/data_loaders.py:940-972),
+    clouds batched through the per-point cloud index."""
+    from eyoc_b200 import synth
+    from eyoc_b200.sparse import voxelize_gpu
+    rng = np.random.default_rng(3)
+    clouds = [(rng.normal(size=(n, 3)) * np.array([30.0, 30.0, 2.0])).astype(np.float32) for n in (50000, 1, 33333)]
+    clouds[0][:100] = clouds[0][100:200]                     # exact duplicates
+    xyz = np.concatenate(clouds)
+    cloud = np.concatenate([np.full(len(c), b, np.int32) for b, c in enumerate(clouds)])
+    coords, sel = voxelize_gpu(torch.from_numpy(xyz).cuda(), 0.3, torch.from_numpy(cloud).cuda())
+    want_c, want_s, off = [], [], 0
+    for b, c in enumerate(clouds):
+        pts, q = synth.voxelize(c, 0.3)
+        key = {tuple(r): i for i, r in reversed(list(enumerate(np.floor(c / np.float32(0.3)).astype(np.int64).tolist())))}
+        s = np.sort(np.fromiter(key.values(), dtype=np.int64))
+        np.testing.assert_array_equal(c[s], pts)
+        want_c.append(np.concatenate([np.full((len(q), 1), b, np.int32), q], 1))
+        want_s.append(s + off)
+        off += len(c)
+    np.testing.assert_array_equal(coords.cpu().numpy(), np.concatenate(want_c))
+    np.testing.assert_array_equal(sel.cpu().numpy(), np.concatenate(want_s))
