@@ -246,8 +246,15 @@ def run_ours(args):
     stage_ev = []
     ev0.record()
     step_ev = [ev0]
+    step_marks = [0]
     for _ in range(K):
+        # the profile entries of the previous step must not keep its kernel maps (GBs) alive: the allocator would have
+        # to cudaMalloc fresh blocks inside the timed region.  Only the last step's entries keep their tables; the
+        # (identical) earlier steps take their pair counts from them.
+        for e in enn.PROFILE[step_marks[-1] if len(step_marks) < 2 else step_marks[-2]: step_marks[-1]]:
+            e[2]['nbr'] = None
         allrec, out = step_resident()
+        step_marks.append(len(enn.PROFILE))
         step_ev.append(torch.cuda.Event(enable_timing=True))
         step_ev[-1].record()
     ev1.record()
@@ -284,6 +291,10 @@ def run_ours(args):
 
     # ---- roofline of the sparse-conv gather-GEMM kernels (events recorded inside the timed region)
     m_cache, tot_ms, tot_bytes, tot_flops, n_tiled = {}, 0.0, 0, 0, 0
+    per_step = step_marks[1] - step_marks[0] if len(step_marks) > 1 else len(prof)
+    for i, (e0, e1, meta) in enumerate(prof):          # every step launches the same sequence on the same coordinates
+        if meta['nbr'] is None and meta['K'] > 1 and per_step:
+            meta['nbr'] = prof[step_marks[-2] + i % per_step][2]['nbr']
     for e0, e1, meta in prof:
         if meta['cin'] % 32 or meta['cout'] % 32 or meta['K'] > 32:
             continue                                            # conv1 (1->32) runs on the generic kernel

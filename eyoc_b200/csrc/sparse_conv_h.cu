@@ -38,6 +38,10 @@ constexpr int NG = 2;          // groups: a warp has about 16 cp.async in flight
 constexpr int WPG = NPW / NG;  // warps per group
 constexpr int RPW = 256 / WPG; // tile rows a warp gathers per item
 constexpr int NI = RPW / 32;   // neighbour indices per lane and item
+// Hand-over of a gathered stage: true = each warp waits (cp.async.wait_group) for its copies of the group's PREVIOUS item
+// and one elected lane arrives; false = every lane's cp.async.mbarrier.arrive.noinc (no waiting, but 32 WPG barrier arrivals
+// per item: an mbarrier arrival is a shared-memory atomic, ~2 cycles each on one address).
+constexpr bool ELECT_ARRIVE = false;
 constexpr int NPT = NPW * 32;
 constexpr int XS_BYTES = TR * 128;             // 32 KB per stage
 constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
@@ -118,7 +122,7 @@ __device__ __forceinline__ void bar_sync_producers() { asm volatile("bar.sync 1,
 // WIDE = false: C_out <= 64, W_hi / W_lo stacked along M (64 lanes each), 4 MMAs per item.  WIDE = true: 128 output
 // channels per CTA (blockIdx.y selects the half when C_out = 256), W_hi and W_lo are separate 128-row operands, 6 MMAs.
 // Thread map: 16 producer warps (also the epilogue), one weight-loader warp, two MMA-issuer warps (one elected thread each).
-template <bool WIDE, int NSW, int NXS>
+template <bool WIDE, int NSW, int NXS, bool DBG>
 __global__ void __launch_bounds__(NPT + 96, 1)
 sparse_conv_h_kernel(HArgs a) {
     constexpr bool PER_TILE = !WIDE;                          // one MMA-issuing thread per tile (see "MMA issuers")
@@ -159,7 +163,7 @@ sparse_conv_h_kernel(HArgs a) {
     const int ntiles = (a.n_out + TR - 1) / TR;
 
     if (tid == 0) {
-        for (int i = 0; i < NXS; ++i) { mbar_init(a_full + 8 * i, 32 * WPG); mbar_init(a_empty + 8 * i, 1); }
+        for (int i = 0; i < NXS; ++i) { mbar_init(a_full + 8 * i, ELECT_ARRIVE ? WPG : 32 * WPG); mbar_init(a_empty + 8 * i, 1); }
         for (int i = 0; i < NSW; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, NMMA); }
         mbar_init(done_bar, NMMA);
         mbar_init_fence();
@@ -243,9 +247,10 @@ sparse_conv_h_kernel(HArgs a) {
     for (int i = tid; i < nitems; i += blockDim.x)
         items[i] = (uint16_t)(items[i] | (((uint32_t)(i / NXS) & 1u) << 10) | ((uint32_t)(i % NXS) << 13));
     __syncthreads();
-    const int ablate = g_ablate;
-    const bool timing = (ablate & 8) && tid == 0 && blockIdx.x < 1024 && blockIdx.y == 0;
-    const bool tracing = (ablate & 16) && blockIdx.x >= 200 && blockIdx.x < 204 && blockIdx.y == 0;
+    // the measurement hooks exist only in the DBG instantiation (launched while eyoc_debug_convh_ablate flags are set)
+    const int ablate = DBG ? g_ablate : 0;
+    const bool timing = DBG && (ablate & 8) && tid == 0 && blockIdx.x < 1024 && blockIdx.y == 0;
+    const bool tracing = DBG && (ablate & 16) && blockIdx.x >= 200 && blockIdx.x < 204 && blockIdx.y == 0;
     const int tcta = blockIdx.x - 200;
     if (timing) { g_times[blockIdx.x][0] = t_start; g_times[blockIdx.x][1] = clock64(); g_times[blockIdx.x][5] = nitems; }
 
@@ -284,13 +289,15 @@ sparse_conv_h_kernel(HArgs a) {
             }
         };
         // rows without a neighbour are zero-filled by the copy itself (source size 0)
+        uint32_t prev_stage = 0xffffffffu;
         auto copy_item = [&](int i, const int (&idx)[NI]) {
             const uint32_t it = items[i];
             const uint32_t s = item_stage(it);
             if (tracing && (warp % WPG) == 0 && lane == 0 && i < 96) g_trace[tcta][i][0] = clock64();
-            if (lane == 0) mbar_wait(a_empty + 8 * s, item_parity(it) ^ 1u);        // the MMAs that last read the stage have completed
+            // every lane waits (one warp-wide instruction): an elected-lane wait would leave the warp divergent for the
+            // compiler, and each of the shuffles below would take its slow WARPSYNC path
+            mbar_wait(a_empty + 8 * s, item_parity(it) ^ 1u);                        // the MMAs that last read the stage have completed
             if (tracing && (warp % WPG) == 0 && lane == 0 && i < 96) g_trace[tcta][i][1] = clock64();
-            __syncwarp();
             if (!(ablate & 2)) {
                 const int ci = item_c(it);
                 const bool first = ci < nch0;
@@ -302,10 +309,20 @@ sparse_conv_h_kernel(HArgs a) {
                     const int v = __shfl_sync(0xffffffffu, idx[q >> 3], ((q & 7) << 2) | rsub);
                     const uint8_t* ptr = src + (uint64_t)(uint32_t)max(v, 0) * cs;
                     const uint32_t dst = ((q & 1) ? st1 : st0) + stage_off + (uint32_t)q * 512u;
-                    cp_async16(dst, ptr, v >= 0 ? 16u : 0u);
+                    cp_async16_or_zero(dst, ptr, v);
                 }
             }
-            cp_async_arrive_noinc(a_full + 8 * s);
+            if (ELECT_ARRIVE) {
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (prev_stage != 0xffffffffu) {         // hand over the group's previous item: its copies had a whole step to land
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(a_full + 8 * prev_stage);
+                }
+                prev_stage = s;
+            } else {
+                cp_async_arrive_noinc(a_full + 8 * s);
+            }
             if (tracing && (warp % WPG) == 0 && lane == 0 && i < 96) g_trace[tcta][i][2] = clock64();
         };
         // Output row of tile row `tid` of each tile, for the epilogue (loaded here so that its latency is long gone).
@@ -331,6 +348,11 @@ sparse_conv_h_kernel(HArgs a) {
                 i = next_own(i1);
                 load_item(i, ia);
                 copy_item(i1, ib);
+            }
+            if (ELECT_ARRIVE && prev_stage != 0xffffffffu) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full + 8 * prev_stage);
             }
         }
         // =========================================================== epilogue: TMEM -> smem transpose -> global
@@ -497,10 +519,17 @@ sparse_conv_h_kernel(HArgs a) {
         // order: the accumulation order of a row stays fixed, results are deterministic) and the two threads' bookkeeping
         // overlaps the other one's MMAs.  A weight slab is released when every issuing thread is past it (a commit from a
         // thread that used the slab, a plain arrival from one that did not).
+        // Barrier waits cost ~250 cycles even when the phase is long complete, so the waits of the NEXT pair (its weight
+        // slab, this thread's item in it) are probed with non-blocking test_wait BEFORE the current item's MMAs are issued:
+        // the probes' latency hides behind the issue, and the blocking wait is only taken when a probe came back negative.
+        // A probe looks one pair ahead at most, which keeps the parity test unambiguous (the stage's previous user lies
+        // >= 3 pairs back, the other issuer is past it: see the static_assert above).
         const int t_own = warp - mma_warp;
         if (lane == 0 && t_own < NMMA) {
             uint32_t w_it = 0, started = 0, ws = 0;
             bool used = false;
+            int pa_idx = -1;                  // item whose "full" barrier was probed / the probe's result
+            uint32_t pa_ok = 0, pw_slab = 0xffffffffu, pw_ok = 0;
             uint32_t it = nitems > 0 ? items[0] : 0u;
             for (int i = 0; i < nitems; ++i) {
                 const uint32_t it_next = i + 1 < nitems ? items[i + 1] : (1u << 12);
@@ -509,7 +538,7 @@ sparse_conv_h_kernel(HArgs a) {
                     // barrier after the completion of that barrier's previous phase
                     ws = w_it % NSW;
                     used = false;
-                    mbar_wait(w_full + 8 * ws, (w_it / NSW) & 1u);
+                    if (!(pw_slab == w_it && pw_ok)) mbar_wait(w_full + 8 * ws, (w_it / NSW) & 1u);
                 }
                 const int t = item_t(it);
                 if (!PER_TILE || t == t_own) {
@@ -518,10 +547,34 @@ sparse_conv_h_kernel(HArgs a) {
                     const uint32_t s = item_stage(it);
                     const uint32_t d = tmem_base + (uint32_t)(t * TR);
                     if (tracing && i < 96) g_trace[tcta][i][3] = clock64();
-                    mbar_wait(a_full + 8 * s, item_parity(it));
+                    if (!(pa_idx == i && pa_ok)) mbar_wait(a_full + 8 * s, item_parity(it));
                     if (tracing && i < 96) g_trace[tcta][i][4] = clock64();
                     fence_proxy_async();                 // the stage was written through the generic proxy (cp.async)
                     tc_fence_after();
+                    // ---- probes for the next pair
+                    {
+                        const int np = (i + 1 < nitems && !item_first(it_next)) ? i + 2 : i + 1;      // a pair has <= 2 items
+                        int jj = -1;
+                        uint32_t cj = 0;
+                        if (!PER_TILE) {
+                            if (i + 1 < nitems) { jj = i + 1; cj = it_next; }
+                        } else if (np < nitems) {
+                            const uint32_t c0 = items[np];
+                            if (item_t(c0) == t_own) { jj = np; cj = c0; }
+                            else if (np + 1 < nitems) {
+                                const uint32_t c1 = items[np + 1];
+                                if (!item_first(c1)) { jj = np + 1; cj = c1; }
+                            }
+                        }
+                        if (np < nitems) {
+                            pw_slab = w_it + 1;
+                            pw_ok = mbar_test(w_full + 8 * ((w_it + 1) % NSW), ((w_it + 1) / NSW) & 1u);
+                        }
+                        if (jj >= 0) {
+                            pa_idx = jj;
+                            pa_ok = mbar_test(a_full + 8 * item_stage(cj), item_parity(cj));
+                        }
+                    }
                     const uint32_t xs = sX + s * XS_BYTES;
                     uint32_t acc = (started >> t) & 1u;
                     if (!(ablate & 1)) {
@@ -640,20 +693,27 @@ __global__ void tile_masks_kernel(const int* __restrict__ nbr, int K, int n_out,
     if (threadIdx.x == 0) masks[blockIdx.x] = m_s;
 }
 
-template <bool WIDE, int NSW, int NXS>
-int launch_h(const HArgs& a, cudaStream_t stream) {
+int h_ablate = 0;      // host copy of g_ablate: non-zero selects the instrumented instantiation
+
+template <bool WIDE, int NSW, int NXS, bool DBG>
+int launch_h2(const HArgs& a, cudaStream_t stream) {
     const size_t smem = (size_t)NXS * XS_BYTES + (size_t)NSW * (WIDE ? 256 : 128) * 128;
-    EYOC_CUDA(cudaFuncSetAttribute(sparse_conv_h_kernel<WIDE, NSW, NXS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EYOC_CUDA(cudaFuncSetAttribute(sparse_conv_h_kernel<WIDE, NSW, NXS, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = (a.n_out + TR - 1) / TR;
     dim3 grid((tiles + NTILE - 1) / NTILE, WIDE ? a.cout / 128 : 1);
-    sparse_conv_h_kernel<WIDE, NSW, NXS><<<grid, NPT + 96, smem, stream>>>(a);
+    sparse_conv_h_kernel<WIDE, NSW, NXS, DBG><<<grid, NPT + 96, smem, stream>>>(a);
     EYOC_LAUNCH_CHECK();
     return EYOC_OK;
+}
+template <bool WIDE, int NSW, int NXS>
+int launch_h(const HArgs& a, cudaStream_t stream) {
+    return h_ablate ? launch_h2<WIDE, NSW, NXS, true>(a, stream) : launch_h2<WIDE, NSW, NXS, false>(a, stream);
 }
 
 }  // namespace
 
 extern "C" int eyoc_debug_convh_ablate(int flags) {
+    h_ablate = flags;
     EYOC_CUDA(cudaMemcpyToSymbol(g_ablate, &flags, sizeof(int)));
     return EYOC_OK;
 }

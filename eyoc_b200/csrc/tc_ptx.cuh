@@ -17,7 +17,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    unsigned long long spins = 0;
+    uint32_t spins = 0;
     while (!done) {
         asm volatile(
             "{\n.reg .pred p;\n"
@@ -26,7 +26,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-        if (!done && ++spins > (1ull << 26)) __trap();      // watchdog: never hang the device
+        if (!done && ++spins > (1u << 26)) __trap();        // watchdog: never hang the device
     }
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -39,6 +39,22 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
 // 16-byte asynchronous copy global -> shared, L2 only; src_bytes = 0 zero-fills the destination
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// the same, zero-filling the destination (and ignoring the source) when row < 0
+__device__ __forceinline__ void cp_async16_or_zero(uint32_t dst, const void* src, int row) {
+    asm volatile("{\n.reg .pred p;\nsetp.lt.s32 p, %2, 0;\ncp.async.cg.shared.global [%0], [%1], 16, p;\n}" ::"r"(dst), "l"(src), "r"(row) : "memory");
+}
+// non-blocking probe of a barrier phase (acquire); the result can be consumed long after the instruction is issued
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
