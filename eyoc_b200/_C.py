@@ -55,7 +55,7 @@ def lib():
         _lib.eyoc_launch_count.restype = ctypes.c_ulonglong
         for name in ('eyoc_knn1_workspace_bytes', 'eyoc_sc2pcr_workspace_bytes', 'eyoc_downsample_workspace_bytes',
                      'eyoc_tile_order_workspace_bytes', 'eyoc_conv_weight_image_floats', 'eyoc_voxelize_workspace_bytes',
-                     'eyoc_convh_weight_image_halves'):
+                     'eyoc_convh_weight_image_halves', 'eyoc_knn1_tc_workspace_bytes'):
             if hasattr(_lib, name):
                 getattr(_lib, name).restype = c_size_t
     return _lib

@@ -11,6 +11,12 @@ import torch
 from .. import _C
 
 
+# 'tc'  : 32-channel descriptors go through the tensor-core pre-filter + exact fp32 re-scoring (eyoc_knn1_tc): the same
+#         indices and values as the fp32-FMA kernel, bit for bit
+# 'fp32': always the fp32-FMA kernel (eyoc_knn1)
+KNN_MODE = 'tc'
+
+
 def knn1(F0, F1, form=0, return_distance=False):
     """Device-side 1-NN.  F0 [B?, N0, D], F1 [B?, N1, D] CUDA fp32 -> int64 [B?, N0] (and fp32 distances)."""
     _C.require_cuda(F0, F1)
@@ -29,12 +35,17 @@ def knn1(F0, F1, form=0, return_distance=False):
             idx, dist0 = idx[0], dist0[0]
         return (idx, dist0) if return_distance else idx
     dist = torch.empty((B, nq), dtype=torch.float32, device=q.device) if return_distance else None
-    ws_bytes = lib.eyoc_knn1_workspace_bytes(_C.c_int(B), _C.c_int64(nq))
+    use_tc = KNN_MODE == 'tc' and nr > 0 and bool(lib.eyoc_knn1_tc_supported(_C.c_int(dim)))
+    if use_tc:
+        ws_bytes = lib.eyoc_knn1_tc_workspace_bytes(_C.c_int(B), _C.c_int64(nq), _C.c_int64(nr))
+    else:
+        ws_bytes = lib.eyoc_knn1_workspace_bytes(_C.c_int(B), _C.c_int64(nq))
     ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=q.device)
+    fn = lib.eyoc_knn1_tc if use_tc else lib.eyoc_knn1
     with torch.cuda.device(q.device):
-        _C.check(lib.eyoc_knn1(_C.ptr(q), _C.ptr(r), _C.c_int(B), _C.c_int64(nq), _C.c_int64(nr), _C.c_int(dim),
-                               _C.c_int(form), _C.ptr(ws), _C.c_size_t(ws.numel()), _C.ptr(idx), _C.ptr(dist),
-                               _C.stream()))
+        _C.check(fn(_C.ptr(q), _C.ptr(r), _C.c_int(B), _C.c_int64(nq), _C.c_int64(nr), _C.c_int(dim),
+                    _C.c_int(form), _C.ptr(ws), _C.c_size_t(ws.numel()), _C.ptr(idx), _C.ptr(dist),
+                    _C.stream()))
     if not batched:
         idx = idx[0]
         dist = dist[0] if dist is not None else None

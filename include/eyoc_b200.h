@@ -41,6 +41,14 @@ unsigned long long eyoc_launch_count(void);
 size_t eyoc_knn1_workspace_bytes(int batch, int64_t nq);
 int eyoc_knn1(const float* q, const float* r, int batch, int64_t nq, int64_t nr, int dim, int form,
               void* workspace, size_t workspace_bytes, int64_t* idx, float* dist, eyoc_stream_t stream);
+/* The same operator for 32-channel descriptors with a tensor-core pre-filter: fp16 scores on tcgen05 with a rigorous
+ * error bound select the few columns per row that can be the exact winner; those are re-scored in eyoc_knn1's fp32-FMA
+ * order, so idx / dist are bit-identical to eyoc_knn1's.  Batches holding non-finite or fp16-overflowing values are
+ * routed to the fp32-FMA kernel on the device. */
+int eyoc_knn1_tc_supported(int dim);
+size_t eyoc_knn1_tc_workspace_bytes(int batch, int64_t nq, int64_t nr);
+int eyoc_knn1_tc(const float* q, const float* r, int batch, int64_t nq, int64_t nr, int dim, int form,
+                 void* workspace, size_t workspace_bytes, int64_t* idx, float* dist, eyoc_stream_t stream);
 
 /* ---------------------------------------------------------------- SC2-PCR estimator
  * Replaces scripts/SC2_PCR/SC2_PCR.py:307-384 Matcher.SC2_PCR (first/second-order spatial
