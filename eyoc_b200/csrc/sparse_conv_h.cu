@@ -38,10 +38,11 @@ constexpr int NG = 2;          // groups: a warp has about 16 cp.async in flight
 constexpr int WPG = NPW / NG;  // warps per group
 constexpr int RPW = 256 / WPG; // tile rows a warp gathers per item
 constexpr int NI = RPW / 32;   // neighbour indices per lane and item
-// Hand-over of a gathered stage: true = each warp waits (cp.async.wait_group) for its copies of the group's PREVIOUS item
-// and one elected lane arrives; false = every lane's cp.async.mbarrier.arrive.noinc (no waiting, but 32 WPG barrier arrivals
-// per item: an mbarrier arrival is a shared-memory atomic, ~2 cycles each on one address).
-constexpr bool ELECT_ARRIVE = false;
+// Every stage has RB "full" and RB "empty" barriers used round-robin by its successive uses (use n of a stage takes
+// barrier n % RB, parity (n / RB) & 1): a parity wait is only ambiguous when the waiter is RB uses = RB * NXS work items
+// away from the barrier's state, far beyond what the rings allow (producers run < NXS + NG items ahead of the slower MMA
+// issuer, the two issuers stay within 2 NSW - 1 items of each other through the weight-slab ring).
+constexpr int RB = 4;
 constexpr int NPT = NPW * 32;
 constexpr int XS_BYTES = TR * 128;             // 32 KB per stage
 constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
@@ -108,14 +109,11 @@ __device__ long long g_trace[4][96][6];
 constexpr int MAX_ITEMS = 27 * 12 * NTILE;      // (kernel offset, 32-channel chunk, tile) work items per CTA
 
 // Work item: bits [0,5) kernel offset, [5,9) chunk index, bit 9 tile, bit 12 = first item of its (offset, chunk),
-// i.e. the MMA side must switch to the next weight slab; bits [13,16) operand stage, bit 10 parity of the stage's "full"
-// barrier for this use.
+// i.e. the MMA side must switch to the next weight slab.  Item i of the list uses operand stage i % NXS.
 __device__ __forceinline__ int item_k(uint32_t it) { return it & 31; }
 __device__ __forceinline__ int item_c(uint32_t it) { return (it >> 5) & 15; }
 __device__ __forceinline__ int item_t(uint32_t it) { return (it >> 9) & 1; }
 __device__ __forceinline__ bool item_first(uint32_t it) { return (it >> 12) & 1; }
-__device__ __forceinline__ uint32_t item_stage(uint32_t it) { return (it >> 13) & 7u; }
-__device__ __forceinline__ uint32_t item_parity(uint32_t it) { return (it >> 10) & 1u; }
 
 __device__ __forceinline__ void bar_sync_producers() { asm volatile("bar.sync 1, %0;" ::"n"(NPT) : "memory"); }
 
@@ -127,11 +125,7 @@ __global__ void __launch_bounds__(NPT + 96, 1)
 sparse_conv_h_kernel(HArgs a) {
     constexpr bool PER_TILE = !WIDE;                          // one MMA-issuing thread per tile (see "MMA issuers")
     constexpr int NMMA = PER_TILE ? NTILE : 1;                // MMA-issuing threads
-    // The producers' and issuers' waits test one parity bit, so nobody may run two phases ahead of a barrier.  With one
-    // issuer, commits are in list order and a group that passed item i - NG (stage freed by item i - NG - NXS) knows item
-    // i - 2 NXS is long committed.  With two issuers the commits of the two tiles interleave, but the weight-slab ring
-    // keeps the issuers within NSW slabs = at most 3 list positions of each other: NXS - NG > 3 keeps the argument intact.
-    static_assert(!PER_TILE || (NXS - NG > 3 && NSW == 2), "stage ring too shallow for two issuers");
+    static_assert(RB * NXS > NXS + NG + 2 * NSW + 2, "barrier rotation too short for the ring depths");
     constexpr int W_BYTES = (WIDE ? 256 : 128) * 128;         // slab: 128 (hi 64 | lo 64) or 256 (hi 128 | lo 128) rows of 128 B
     // instruction descriptor: D = fp32 (bit 4), A = B = fp16 (format 0), both K-major, N = 256, M = 128
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TR >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -140,7 +134,7 @@ sparse_conv_h_kernel(HArgs a) {
     const uint32_t sX = smem_u32(smem_raw) + smem_off;           // NXS stages; reused by the epilogue transpose
     const uint32_t sW = sX + NXS * XS_BYTES;                     // NSW slabs
     float* const sOut = reinterpret_cast<float*>(smem_raw + smem_off);
-    __shared__ uint64_t bars[2 * NXS + 2 * NSW + 1];
+    __shared__ uint64_t bars[2 * NXS * RB + 2 * NSW + 1];
     __shared__ uint32_t tmem_base_s;
     __shared__ uint32_t valid[NTILE];
     __shared__ uint32_t tmask[32];
@@ -155,15 +149,15 @@ sparse_conv_h_kernel(HArgs a) {
     const int nparts = WIDE ? a.cout / 128 : 1;
     const int part = WIDE ? blockIdx.y : 0;
     const int cpart = WIDE ? 128 : a.cout;                       // output channels this CTA produces
-    const uint32_t a_full = smem_u32(&bars[0]), a_empty = smem_u32(&bars[NXS]);
-    const uint32_t w_full = smem_u32(&bars[2 * NXS]), w_empty = smem_u32(&bars[2 * NXS + NSW]);
-    const uint32_t done_bar = smem_u32(&bars[2 * NXS + 2 * NSW]);
+    const uint32_t a_full = smem_u32(&bars[0]), a_empty = smem_u32(&bars[NXS * RB]);
+    const uint32_t w_full = smem_u32(&bars[2 * NXS * RB]), w_empty = smem_u32(&bars[2 * NXS * RB + NSW]);
+    const uint32_t done_bar = smem_u32(&bars[2 * NXS * RB + 2 * NSW]);
     const int wload_warp = NPW, mma_warp = NPW + 1;
     const int tile0 = blockIdx.x * NTILE;
     const int ntiles = (a.n_out + TR - 1) / TR;
 
     if (tid == 0) {
-        for (int i = 0; i < NXS; ++i) { mbar_init(a_full + 8 * i, ELECT_ARRIVE ? WPG : 32 * WPG); mbar_init(a_empty + 8 * i, 1); }
+        for (int i = 0; i < NXS * RB; ++i) { mbar_init(a_full + 8 * i, 32 * WPG); mbar_init(a_empty + 8 * i, 1); }
         for (int i = 0; i < NSW; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, NMMA); }
         mbar_init(done_bar, NMMA);
         mbar_init_fence();
@@ -243,10 +237,6 @@ sparse_conv_h_kernel(HArgs a) {
     }
     __syncthreads();
     const int nitems = nitems_s;
-    // ---- operand stage of every item: one ring of NXS stages in list order
-    for (int i = tid; i < nitems; i += blockDim.x)
-        items[i] = (uint16_t)(items[i] | (((uint32_t)(i / NXS) & 1u) << 10) | ((uint32_t)(i % NXS) << 13));
-    __syncthreads();
     // the measurement hooks exist only in the DBG instantiation (launched while eyoc_debug_convh_ablate flags are set)
     const int ablate = DBG ? g_ablate : 0;
     const bool timing = DBG && (ablate & 8) && tid == 0 && blockIdx.x < 1024 && blockIdx.y == 0;
@@ -289,15 +279,14 @@ sparse_conv_h_kernel(HArgs a) {
             }
         };
         // rows without a neighbour are zero-filled by the copy itself (source size 0)
-        uint32_t prev_stage = 0xffffffffu;
         auto copy_item = [&](int i, const int (&idx)[NI]) {
             const uint32_t it = items[i];
-            const uint32_t s = item_stage(it);
-            if (tracing && (warp % WPG) == 0 && lane == 0 && i < 96) g_trace[tcta][i][0] = clock64();
+            const uint32_t s = (uint32_t)(i % NXS), n = (uint32_t)(i / NXS);     // stage and which use of it this is
+            if (tracing && !(ablate & 128) && (warp % WPG) == 0 && lane == 0 && i < 96) g_trace[tcta][i][0] = clock64();
             // every lane waits (one warp-wide instruction): an elected-lane wait would leave the warp divergent for the
             // compiler, and each of the shuffles below would take its slow WARPSYNC path
-            mbar_wait(a_empty + 8 * s, item_parity(it) ^ 1u);                        // the MMAs that last read the stage have completed
-            if (tracing && (warp % WPG) == 0 && lane == 0 && i < 96) g_trace[tcta][i][1] = clock64();
+            if (n > 0) mbar_wait(a_empty + 8 * (s * RB + (n - 1) % RB), ((n - 1) / RB) & 1u);    // the MMAs of its previous use have completed
+            if (tracing && !(ablate & 128) && (warp % WPG) == 0 && lane == 0 && i < 96) g_trace[tcta][i][1] = clock64();
             if (!(ablate & 2)) {
                 const int ci = item_c(it);
                 const bool first = ci < nch0;
@@ -312,18 +301,8 @@ sparse_conv_h_kernel(HArgs a) {
                     cp_async16_or_zero(dst, ptr, v);
                 }
             }
-            if (ELECT_ARRIVE) {
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                if (prev_stage != 0xffffffffu) {         // hand over the group's previous item: its copies had a whole step to land
-                    asm volatile("cp.async.wait_group 1;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(a_full + 8 * prev_stage);
-                }
-                prev_stage = s;
-            } else {
-                cp_async_arrive_noinc(a_full + 8 * s);
-            }
-            if (tracing && (warp % WPG) == 0 && lane == 0 && i < 96) g_trace[tcta][i][2] = clock64();
+            cp_async_arrive_noinc(a_full + 8 * (s * RB + n % RB));
+            if (tracing && !(ablate & 128) && (warp % WPG) == 0 && lane == 0 && i < 96) g_trace[tcta][i][2] = clock64();
         };
         // Output row of tile row `tid` of each tile, for the epilogue (loaded here so that its latency is long gone).
         int orow[NTILE];
@@ -348,11 +327,6 @@ sparse_conv_h_kernel(HArgs a) {
                 i = next_own(i1);
                 load_item(i, ia);
                 copy_item(i1, ib);
-            }
-            if (ELECT_ARRIVE && prev_stage != 0xffffffffu) {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(a_full + 8 * prev_stage);
             }
         }
         // =========================================================== epilogue: TMEM -> smem transpose -> global
@@ -544,10 +518,10 @@ sparse_conv_h_kernel(HArgs a) {
                 if (!PER_TILE || t == t_own) {
                     used = true;
                     const uint32_t wh = sW + ws * W_BYTES;
-                    const uint32_t s = item_stage(it);
+                    const uint32_t s = (uint32_t)(i % NXS), n = (uint32_t)(i / NXS);
                     const uint32_t d = tmem_base + (uint32_t)(t * TR);
                     if (tracing && i < 96) g_trace[tcta][i][3] = clock64();
-                    if (!(pa_idx == i && pa_ok)) mbar_wait(a_full + 8 * s, item_parity(it));
+                    if (!(pa_idx == i && pa_ok)) mbar_wait(a_full + 8 * (s * RB + n % RB), (n / RB) & 1u);
                     if (tracing && i < 96) g_trace[tcta][i][4] = clock64();
                     fence_proxy_async();                 // the stage was written through the generic proxy (cp.async)
                     tc_fence_after();
@@ -571,25 +545,28 @@ sparse_conv_h_kernel(HArgs a) {
                             pw_ok = mbar_test(w_full + 8 * ((w_it + 1) % NSW), ((w_it + 1) / NSW) & 1u);
                         }
                         if (jj >= 0) {
+                            const uint32_t sj = (uint32_t)(jj % NXS), nj = (uint32_t)(jj / NXS);
                             pa_idx = jj;
-                            pa_ok = mbar_test(a_full + 8 * item_stage(cj), item_parity(cj));
+                            pa_ok = mbar_test(a_full + 8 * (sj * RB + nj % RB), (nj / RB) & 1u);
                         }
                     }
                     const uint32_t xs = sX + s * XS_BYTES;
                     uint32_t acc = (started >> t) & 1u;
+                    if (tracing && (ablate & 128) && i < 96) g_trace[tcta][i][0] = clock64();      // probes issued
                     if (!(ablate & 1)) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {                        // virtual channels: j = 0, 1 x_hi; j = 2, 3 x_lo'
                             umma_f16(d, make_desc_sw128(wh + j * 32), make_desc_sw128(xs + j * 32), IDESC, acc);
                             acc = 1u;
                         }
+                        if (tracing && (ablate & 128) && i < 96) g_trace[tcta][i][1] = clock64();  // MMAs issued
                         if (WIDE) {
 #pragma unroll
                             for (int j = 0; j < 2; ++j)                      // W_lo x_hi
                                 umma_f16(d, make_desc_sw128(wh + 128 * 128 + j * 32), make_desc_sw128(xs + j * 32), IDESC, 1u);
                         }
                     }
-                    umma_commit(a_empty + 8 * s);
+                    umma_commit(a_empty + 8 * (s * RB + n % RB));
                     started |= 1u << t;
                     if (tracing && i < 96) g_trace[tcta][i][5] = clock64();
                 }
@@ -597,6 +574,7 @@ sparse_conv_h_kernel(HArgs a) {
                     if (used) umma_commit(w_empty + 8 * ws);
                     else mbar_arrive(w_empty + 8 * ws);
                     ++w_it;
+                    if (tracing && (ablate & 128) && i < 96) g_trace[tcta][i][2] = clock64();      // slab released
                 }
                 it = it_next;
             }
