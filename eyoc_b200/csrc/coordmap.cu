@@ -53,6 +53,41 @@ __device__ __forceinline__ int hash_lookup(const unsigned long long* __restrict_
     }
 }
 
+// Lookups of one x-row of kernel offsets (KS keys) with all home-slot loads in flight together: the map kernels are
+// bound by the latency of dependent random accesses (hash -> key -> value), so a thread that issues its KS independent
+// key loads back to back, then its value loads, hides most of it.  Collisions fall back to linear probing.
+template <int KS>
+__device__ __forceinline__ void hash_lookup_row(const unsigned long long* __restrict__ keys, const int* __restrict__ vals, long long cap,
+                                                const unsigned long long (&key)[KS], const bool (&act)[KS], int (&v)[KS]) {
+    long long slot[KS];
+    unsigned long long got[KS];
+#pragma unroll
+    for (int j = 0; j < KS; ++j) {
+        slot[j] = (long long)(mix64(key[j]) & (unsigned long long)(cap - 1));
+        got[j] = EMPTY;
+    }
+#pragma unroll
+    for (int j = 0; j < KS; ++j)
+        if (act[j]) got[j] = keys[slot[j]];
+#pragma unroll
+    for (int j = 0; j < KS; ++j) v[j] = -1;
+#pragma unroll
+    for (int j = 0; j < KS; ++j)
+        if (act[j] && got[j] == key[j]) v[j] = vals[slot[j]];
+#pragma unroll
+    for (int j = 0; j < KS; ++j) {
+        if (act[j] && got[j] != key[j] && got[j] != EMPTY) {          // home slot taken by another key: probe on
+            long long sl = (slot[j] + 1) & (cap - 1);
+            while (true) {
+                const unsigned long long k = keys[sl];
+                if (k == key[j]) { v[j] = vals[sl]; break; }
+                if (k == EMPTY) break;
+                sl = (sl + 1) & (cap - 1);
+            }
+        }
+    }
+}
+
 __global__ void hash_clear_kernel(unsigned long long* keys, int* vals, long long cap) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < cap) { keys[i] = EMPTY; vals[i] = 0x7fffffff; }
@@ -184,19 +219,31 @@ __global__ void down_emit_kernel(const int* __restrict__ coords, int n, int ts_o
     vals[slot] = row;
 }
 
-// nbr[k, o] = row in the input map of  c_o + off_k * step
+// nbr[k, o] = row in the input map of  c_o + off_k * step.  One thread handles a whole x-row of kernel offsets
+// (blockIdx.y = iy + KS * iz) with its KS lookups in flight together.
+template <int KS>
 __global__ void kernel_map_kernel(const int* __restrict__ out_coords, int n_out, const unsigned long long* __restrict__ keys,
-                                  const int* __restrict__ vals, long long cap, int ksize, int step, int* __restrict__ nbr) {
+                                  const int* __restrict__ vals, long long cap, int step, int* __restrict__ nbr) {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
-    const int k = blockIdx.y;
+    const int rj = blockIdx.y;
     if (o >= n_out) return;
-    const int r = (ksize - 1) / 2;
-    const int ix = k % ksize - r, iy = (k / ksize) % ksize - r, iz = k / (ksize * ksize) - r;
+    constexpr int r = (KS - 1) / 2;
+    const int iy = rj % KS - r, iz = rj / KS - r;
     const int4 c = reinterpret_cast<const int4*>(out_coords)[o];
-    const int x = c.y + ix * step, y = c.z + iy * step, z = c.w + iz * step;
-    int v = -1;
-    if (in_range16(x) && in_range16(y) && in_range16(z)) v = hash_lookup(keys, vals, cap, pack4(c.x, x, y, z));
-    nbr[(size_t)k * n_out + o] = v;
+    const int y = c.z + iy * step, z = c.w + iz * step;
+    const bool yz_ok = in_range16(y) && in_range16(z);
+    unsigned long long key[KS];
+    bool act[KS];
+    int v[KS];
+#pragma unroll
+    for (int j = 0; j < KS; ++j) {
+        const int x = c.y + (j - r) * step;
+        act[j] = yz_ok && in_range16(x);
+        key[j] = pack4(c.x, x, y, z);
+    }
+    hash_lookup_row<KS>(keys, vals, cap, key, act, v);
+#pragma unroll
+    for (int j = 0; j < KS; ++j) nbr[(size_t)(rj * KS + j) * n_out + o] = v[j];
 }
 
 // Voxelisation (lib/data_loaders.py:936-979): q = floor(xyz / voxel_size) evaluated as torch / numpy do in fp32 (true
@@ -217,22 +264,35 @@ __global__ void quantize_kernel(const float* __restrict__ xyz, const int* __rest
 // Stride-1 map of a coordinate set onto itself: offsets come in mirrored pairs (k, K^3-1-k) and i = nbr[k, o] <=>
 // o = nbr[K^3-1-k, i], so only the first half of the offsets is probed; every hit is written twice (the table is
 // pre-filled with -1 and the centre offset is the identity).
+template <int KS>
 __global__ void kernel_map_sym_kernel(const int* __restrict__ coords, int n, const unsigned long long* __restrict__ keys,
-                                      const int* __restrict__ vals, long long cap, int ksize, int step, int* __restrict__ nbr) {
+                                      const int* __restrict__ vals, long long cap, int step, int* __restrict__ nbr) {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
-    const int k = blockIdx.y;                       // 0 .. K^3/2 (the last one is the centre)
+    const int rj = blockIdx.y;                      // x-row of offsets: k = rj * KS + j, rows 0 .. (K^3 / 2) / KS
     if (o >= n) return;
-    const int K3 = ksize * ksize * ksize;
-    if (k == K3 / 2) { nbr[(size_t)k * n + o] = o; return; }
-    const int r = (ksize - 1) / 2;
-    const int ix = k % ksize - r, iy = (k / ksize) % ksize - r, iz = k / (ksize * ksize) - r;
+    constexpr int K3 = KS * KS * KS, r = (KS - 1) / 2;
+    const int iy = rj % KS - r, iz = rj / KS - r;
     const int4 c = reinterpret_cast<const int4*>(coords)[o];
-    const int x = c.y + ix * step, y = c.z + iy * step, z = c.w + iz * step;
-    if (!(in_range16(x) && in_range16(y) && in_range16(z))) return;
-    const int v = hash_lookup(keys, vals, cap, pack4(c.x, x, y, z));
-    if (v >= 0) {
-        nbr[(size_t)k * n + o] = v;
-        nbr[(size_t)(K3 - 1 - k) * n + v] = o;
+    const int y = c.z + iy * step, z = c.w + iz * step;
+    const bool yz_ok = in_range16(y) && in_range16(z);
+    unsigned long long key[KS];
+    bool act[KS];
+    int v[KS];
+#pragma unroll
+    for (int j = 0; j < KS; ++j) {
+        const int x = c.y + (j - r) * step;
+        act[j] = rj * KS + j < K3 / 2 && yz_ok && in_range16(x);        // first half of the offsets only
+        key[j] = pack4(c.x, x, y, z);
+    }
+    hash_lookup_row<KS>(keys, vals, cap, key, act, v);
+#pragma unroll
+    for (int j = 0; j < KS; ++j) {
+        const int k = rj * KS + j;
+        if (k == K3 / 2) nbr[(size_t)k * n + o] = o;                     // the centre offset is the identity
+        else if (k < K3 / 2 && v[j] >= 0) {
+            nbr[(size_t)k * n + o] = v[j];
+            nbr[(size_t)(K3 - 1 - k) * n + v[j]] = o;
+        }
     }
 }
 
@@ -415,9 +475,14 @@ extern "C" int eyoc_kernel_map(const int32_t* out_coords, int64_t n_out, const u
     EYOC_CHECK_ARG(ksize >= 1 && (ksize & 1) && ksize <= 7, "eyoc_kernel_map: kernel size must be odd and <= 7 (got %d)", ksize);
     EYOC_CHECK_ARG(n_out >= 0 && n_out < (1ll << 31), "eyoc_kernel_map: bad n_out");
     if (n_out == 0) return EYOC_OK;
-    dim3 grid((unsigned)((n_out + 255) / 256), ksize * ksize * ksize);
-    kernel_map_kernel<<<grid, 256, 0, stream>>>(out_coords, (int)n_out, (const unsigned long long*)in_table_keys, in_table_vals, capacity,
-                                                ksize, step, nbr);
+    dim3 grid((unsigned)((n_out + 255) / 256), ksize * ksize);
+    const unsigned long long* tk = (const unsigned long long*)in_table_keys;
+    switch (ksize) {
+        case 1: kernel_map_kernel<1><<<grid, 256, 0, stream>>>(out_coords, (int)n_out, tk, in_table_vals, capacity, step, nbr); break;
+        case 3: kernel_map_kernel<3><<<grid, 256, 0, stream>>>(out_coords, (int)n_out, tk, in_table_vals, capacity, step, nbr); break;
+        case 5: kernel_map_kernel<5><<<grid, 256, 0, stream>>>(out_coords, (int)n_out, tk, in_table_vals, capacity, step, nbr); break;
+        default: kernel_map_kernel<7><<<grid, 256, 0, stream>>>(out_coords, (int)n_out, tk, in_table_vals, capacity, step, nbr); break;
+    }
     EYOC_LAUNCH_CHECK();
     return EYOC_OK;
 }
@@ -430,9 +495,14 @@ extern "C" int eyoc_kernel_map_self(const int32_t* coords, int64_t n, const uint
     if (n == 0) return EYOC_OK;
     const int K3 = ksize * ksize * ksize;
     EYOC_CUDA(cudaMemsetAsync(nbr, 0xff, (size_t)K3 * n * sizeof(int32_t), stream));
-    dim3 grid((unsigned)((n + 255) / 256), K3 / 2 + 1);
-    kernel_map_sym_kernel<<<grid, 256, 0, stream>>>(coords, (int)n, (const unsigned long long*)table_keys, table_vals, capacity, ksize,
-                                                    step, nbr);
+    dim3 grid((unsigned)((n + 255) / 256), (K3 / 2) / ksize + 1);
+    const unsigned long long* tk = (const unsigned long long*)table_keys;
+    switch (ksize) {
+        case 1: kernel_map_sym_kernel<1><<<grid, 256, 0, stream>>>(coords, (int)n, tk, table_vals, capacity, step, nbr); break;
+        case 3: kernel_map_sym_kernel<3><<<grid, 256, 0, stream>>>(coords, (int)n, tk, table_vals, capacity, step, nbr); break;
+        case 5: kernel_map_sym_kernel<5><<<grid, 256, 0, stream>>>(coords, (int)n, tk, table_vals, capacity, step, nbr); break;
+        default: kernel_map_sym_kernel<7><<<grid, 256, 0, stream>>>(coords, (int)n, tk, table_vals, capacity, step, nbr); break;
+    }
     EYOC_LAUNCH_CHECK();
     return EYOC_OK;
 }
