@@ -190,18 +190,28 @@ sparse_conv_cin1_kernel(ConvArgs a) {
     float acc[COUT];
 #pragma unroll
     for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
-    for (int k = 0; k < a.K; ++k) {
-        const int v = a.nbr ? __ldg(a.nbr + (size_t)k * a.n_out + r) : r;
-        if (v < 0) continue;
-        const float x = __ldg(a.in0 + v);
-        const float4* w4 = reinterpret_cast<const float4*>(wsm + k * COUT);
+    // The two dependent loads per offset (table entry, then the neighbour's feature) are issued five offsets at a time
+    // so that their latencies overlap; the accumulation order (k ascending, missing neighbours skipped) is unchanged.
+    constexpr int U = 5;
+    for (int k0 = 0; k0 < a.K; k0 += U) {
+        int v[U];
+        float x[U];
 #pragma unroll
-        for (int c = 0; c < COUT / 4; ++c) {
-            const float4 w = w4[c];
-            acc[4 * c + 0] = __fmaf_rn(x, w.x, acc[4 * c + 0]);
-            acc[4 * c + 1] = __fmaf_rn(x, w.y, acc[4 * c + 1]);
-            acc[4 * c + 2] = __fmaf_rn(x, w.z, acc[4 * c + 2]);
-            acc[4 * c + 3] = __fmaf_rn(x, w.w, acc[4 * c + 3]);
+        for (int u = 0; u < U; ++u) v[u] = k0 + u < a.K ? (a.nbr ? __ldg(a.nbr + (size_t)(k0 + u) * a.n_out + r) : r) : -1;
+#pragma unroll
+        for (int u = 0; u < U; ++u) x[u] = v[u] >= 0 ? __ldg(a.in0 + v[u]) : 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (v[u] < 0) continue;
+            const float4* w4 = reinterpret_cast<const float4*>(wsm + (k0 + u) * COUT);
+#pragma unroll
+            for (int c = 0; c < COUT / 4; ++c) {
+                const float4 w = w4[c];
+                acc[4 * c + 0] = __fmaf_rn(x[u], w.x, acc[4 * c + 0]);
+                acc[4 * c + 1] = __fmaf_rn(x[u], w.y, acc[4 * c + 1]);
+                acc[4 * c + 2] = __fmaf_rn(x[u], w.z, acc[4 * c + 2]);
+                acc[4 * c + 3] = __fmaf_rn(x[u], w.w, acc[4 * c + 3]);
+            }
         }
     }
     float ss = 0.f;
