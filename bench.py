@@ -315,8 +315,14 @@ def run_ours(args):
                   f'ms/launch={d[1] / d[0]:8.3f} algGB/s={d[2] / d[1] / 1e6:8.1f} TFLOP/s={d[3] / d[1] / 1e9:7.2f}', file=sys.stderr)
     peak, peak_src = _peaks()
     achieved = tot_bytes / (tot_ms / 1e3) / 1e9 if tot_ms > 0 else 0.0
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch of the captured shape)
+    traffic, traffic_note = None, None
+    tp = os.path.join(ROOT, 'profiles', 'ncu_conv_h_traffic.json')
+    if enn.CONV_MODE == 'f16x3' and os.path.exists(tp):
+        tj = json.load(open(tp))
+        traffic, traffic_note = tj['dram_bytes_per_launch'], tj['note']
     roofline = {'bound': 'hbm', 'kernel': ('sparse_conv_h_kernel' if enn.CONV_MODE == 'f16x3' else 'sparse_conv_tc_kernel') + ' (all tensor-core sparse-conv launches of the timed region)',
-                'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'traffic_note': traffic_note,
                 'peak_source': peak_src, 'launches_timed': n_tiled, 'avg_launch_ms': tot_ms / max(n_tiled, 1),
                 'share_of_step': tot_ms / ms if ms > 0 else None,
                 'algorithmic_bytes_per_step': tot_bytes // max(K, 1), 'achieved_tflops_fp32': tot_flops / (tot_ms / 1e3) / 1e12 if tot_ms > 0 else 0.0}
@@ -367,10 +373,18 @@ def main():
     if args.gpus > 1 and 'RANK' not in os.environ:        # convenience: self-launch one rank per GPU
         os.execvp(sys.executable, [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
                                    '--master-addr', '127.0.0.1', '--master-port', '29517', os.path.abspath(__file__)] + sys.argv[1:])
+    # libraries (NCCL's version banner, ...) may write to the C-level stdout: keep the contract's ONE JSON line clean by
+    # pointing fd 1 at stderr while the benchmark runs and restoring it for the final print
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved_fd, 'w')
+    sys.stdout = real_stdout
     if args.impl == 'reference':
         run_reference(args)
     else:
         run_ours(args)
+    real_stdout.flush()
 
 
 if __name__ == '__main__':

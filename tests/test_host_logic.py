@@ -133,3 +133,25 @@ def test_fast_planner_is_numpy_exact():
     np.random.seed(1)
     c = pipe.plan([(300, 700)], fast=True)
     assert len(c['fc0'][0]) == 300 and c['src'].shape == (1, 800)
+
+
+def test_test_kitti_cli_and_config():
+    """The drop-in driver keeps the reference's flags (scripts/test_kitti.py:240-292) and merges config_KITTI.json when
+    SC2-PCR is selected; RANSAC (the reference default) is refused because Open3D is outside the hot path."""
+    import json
+    import os
+    import pytest
+    from eyoc_b200.scripts import test_kitti as tk
+    args = tk.parse_args(['--use_RANSAC', 'false', '--rte_thresh', '0.6', '--rre_thresh', '1.5', '--pair_min_dist', '5',
+                          '--pair_max_dist', '20', '--LoKITTI', 'true'])
+    cfg = tk.make_config(args)
+    ref_json = '/root/reference/scripts/SC2_PCR/config_json/config_KITTI.json'
+    if os.path.exists(ref_json):                      # the constants are the reference's own (checked where it is mounted)
+        assert tk.CONFIG_KITTI == json.load(open(ref_json))
+    assert cfg.num_node == 8000 and cfg.k1 == 30 and cfg.use_mutual is False
+    assert cfg.rte_thresh == 0.6 and cfg.rre_thresh == 1.5 and cfg.pair_min_dist == 5 and cfg.LoKITTI is True
+    assert cfg.model == 'ResUNetBN2C' and cfg.conv1_kernel_size == 5 and cfg.model_n_out == 32
+    default = tk.make_config(tk.parse_args([]))
+    assert default.use_RANSAC is True and 'num_node' not in default
+    with pytest.raises(NotImplementedError):
+        tk.main(default, [])
