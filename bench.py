@@ -198,6 +198,9 @@ def run_ours(args):
         enn.CONV_MODE = args.conv_mode
     if args.no_tile_order:
         enn.TILE_ORDER = False
+    if args.tile_group_mb:
+        from eyoc_b200 import sparse as esp
+        esp.TILE_GROUP_BYTES = args.tile_group_mb * 1e6
     P = args.pairs_per_gpu
     K, W = args.steps, max(args.warmup, 3)
     pairs = synth.make_pairs(list(range(rank * P, rank * P + P)))
@@ -369,6 +372,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--conv-breakdown', action='store_true')
     ap.add_argument('--no-tile-order', action='store_true')
+    ap.add_argument('--tile-group-mb', type=float, default=None, help='L2 budget of one cloud group of the tile order (sparse.TILE_GROUP_BYTES)')
     args = ap.parse_args()
     if args.gpus > 1 and 'RANK' not in os.environ:        # convenience: self-launch one rank per GPU
         os.execvp(sys.executable, [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',

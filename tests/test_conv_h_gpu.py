@@ -159,3 +159,30 @@ def test_forward_f16x3_vs_oracle():
     assert raw._F is None and raw._Fh is not None
     want_raw = RO.resunet_forward(coords, feats, sd, False, 5)
     assert float((raw.F.cpu() - want_raw).abs().max()) <= 1e-5 * max(1.0, float(want_raw.abs().max()))
+
+
+def test_forward_fat_variant_vs_oracle():
+    """ResUNetFatBN (model/resunet.py:224-227, the model of scripts/test_waymo.sh:13): TR_CHANNELS [_, 128, 128, 128, 256],
+    i.e. a 12-chunk 384-channel concat and 256-channel transposed convolutions - same kernels, different channel table."""
+    from eyoc_b200.model import load_model
+    from eyoc_b200.sparse import SparseTensor
+    from oracle import resunet_oracle as RO
+    from tests.test_resunet_gpu import _cloud
+    coords = _cloud(2500, 4, batch=2)
+    feats = torch.ones((len(coords), 1), dtype=torch.float32)
+    torch.manual_seed(9)
+    model = load_model('ResUNetFatBN')(1, 32, bn_momentum=0.05, normalize_feature=True, conv1_kernel_size=5, D=3)
+    g = torch.Generator().manual_seed(10)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+                m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    assert sd['conv3_tr.kernel'].shape == (27, 384, 128) and sd['conv4_tr.kernel'].shape == (27, 256, 256)
+    want = RO.resunet_forward(coords, feats, sd, True, 5)
+    model = model.cuda().eval()
+    got = model(SparseTensor(feats.cuda(), coordinates=torch.from_numpy(coords).cuda())).F.cpu()
+    assert float((got - want).abs().max()) <= 1e-5, float((got - want).abs().max())
