@@ -320,14 +320,50 @@ __global__ void parity_class_kernel(const int* __restrict__ coords, int n, int t
 // (tile, offset) items of the tensor-core convolution are either skipped or densely filled, while a group of
 // clouds (the L2 working set of the gather) stays contiguous.
 __global__ void tile_key_kernel(const int* __restrict__ nbr, int K, int n_out, const int* __restrict__ coords, int group,
-                                unsigned long long* __restrict__ keys, int* __restrict__ iota) {
+                                unsigned long long* __restrict__ keys, int* __restrict__ iota, unsigned int* __restrict__ hist) {
+    __shared__ unsigned int h_s[32];
+    if (threadIdx.x < 32) h_s[threadIdx.x] = 0;
+    __syncthreads();
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int m = 0;
+    if (o < n_out) {
+        for (int k = 0; k < K; ++k) m |= (unsigned int)(__ldg(nbr + (size_t)k * n_out + o) >= 0) << k;
+        const int b = coords[4 * (size_t)o];
+        keys[o] = ((unsigned long long)(unsigned int)(b / group) << 27) | m;
+        iota[o] = o;
+    }
+    // how many rows have a neighbour at each offset (decides the significance of the offsets in the sort key)
+    for (int k = 0; k < K; ++k) {
+        const unsigned int c = __popc(__ballot_sync(0xffffffffu, (m >> k) & 1u));
+        if ((threadIdx.x & 31) == 0 && c) atomicAdd(&h_s[k], c);
+    }
+    __syncthreads();
+    if (threadIdx.x < K && h_s[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h_s[threadIdx.x]);
+}
+
+// pos[k] = bit position of offset k in the sort key: offsets ordered by (count ascending, k ascending), the RAREST offset in
+// the most significant bit.  Rows then cluster first by the offsets few rows have, and the 256-row tiles cut from the sorted
+// order execute ~6 % fewer (tile, offset) items than with the offsets in natural significance (tools/tile_fill.py).
+__global__ void tile_bit_order_kernel(const unsigned int* __restrict__ hist, int K, int* __restrict__ pos) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int k = 0; k < K; ++k) {
+        int rank = 0;
+        for (int j = 0; j < K; ++j) rank += (hist[j] < hist[k]) || (hist[j] == hist[k] && j < k);
+        pos[k] = K - 1 - rank;
+    }
+}
+
+__global__ void tile_key_remap_kernel(unsigned long long* __restrict__ keys, int n_out, int K, const int* __restrict__ pos) {
+    __shared__ int p_s[32];
+    if (threadIdx.x < 32) p_s[threadIdx.x] = threadIdx.x < K ? pos[threadIdx.x] : 0;
+    __syncthreads();
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= n_out) return;
-    unsigned int m = 0;
-    for (int k = 0; k < K; ++k) m |= (unsigned int)(__ldg(nbr + (size_t)k * n_out + o) >= 0) << k;
-    const int b = coords[4 * (size_t)o];
-    keys[o] = ((unsigned long long)(unsigned int)(b / group) << 27) | m;
-    iota[o] = o;
+    const unsigned long long key = keys[o];
+    const unsigned int m = (unsigned int)(key & 0x7ffffffull);
+    unsigned int r = 0;
+    for (int k = 0; k < K; ++k) r |= ((m >> k) & 1u) << p_s[k];
+    keys[o] = (key & ~0x7ffffffull) | r;
 }
 
 __global__ void permute_columns_kernel(const int* __restrict__ nbr, int n_out, const int* __restrict__ perm, int* __restrict__ out) {
@@ -343,7 +379,7 @@ extern "C" size_t eyoc_tile_order_workspace_bytes(int64_t n_out) {
     size_t temp = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, temp, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const int*)nullptr,
                                     (int*)nullptr, (int)n_out, 0, 43);
-    return 2 * eyoc_align((size_t)n_out * 8) + eyoc_align((size_t)n_out * 4) + eyoc_align(temp) + 256;
+    return 2 * eyoc_align((size_t)n_out * 8) + eyoc_align((size_t)n_out * 4) + eyoc_align(temp) + 1024;
 }
 
 extern "C" int eyoc_tile_order(const int32_t* nbr, int K, int64_t n_out, const int32_t* out_coords, int group_clouds, int max_batch,
@@ -364,7 +400,14 @@ extern "C" int eyoc_tile_order(const int32_t* nbr, int K, int64_t n_out, const i
     cub::DeviceRadixSort::SortPairs(nullptr, temp, keys, keys2, iota, row_perm, (int)n_out, 0, 43);
     void* tmp = c.take<char>(temp);
     const unsigned g = (unsigned)((n_out + 255) / 256);
-    tile_key_kernel<<<g, 256, 0, stream>>>(nbr, K, (int)n_out, out_coords, group_clouds, keys, iota);
+    unsigned int* hist = c.take<unsigned int>(32);
+    int* pos = c.take<int>(32);
+    EYOC_CUDA(cudaMemsetAsync(hist, 0, 32 * sizeof(unsigned int), stream));
+    tile_key_kernel<<<g, 256, 0, stream>>>(nbr, K, (int)n_out, out_coords, group_clouds, keys, iota, hist);
+    EYOC_LAUNCH_CHECK();
+    tile_bit_order_kernel<<<1, 32, 0, stream>>>(hist, K, pos);
+    EYOC_LAUNCH_CHECK();
+    tile_key_remap_kernel<<<g, 256, 0, stream>>>(keys, (int)n_out, K, pos);
     EYOC_LAUNCH_CHECK();
     int gbits = 0;
     while ((max_batch / group_clouds) >> gbits) ++gbits;

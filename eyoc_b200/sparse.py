@@ -38,8 +38,10 @@ class CoordinateMapKey:
         return f'CoordinateMapKey(tensor_stride={self.tensor_stride})'
 
 
-# L2 budget (bytes of input features) of one cloud group of the tile order (B200: 126 MB L2, shared with the outputs).
-TILE_GROUP_BYTES = 48e6
+# Budget (bytes of input features) of one cloud group of the tile order.  Measured on B200 (bench.py --tile-group-mb): the
+# gather is not L2 / DRAM bound (L2 throughput 21 %, DRAM 11 %), so denser tiles beat a smaller L2 working set - 24 MB:
+# 54 % of the HBM roofline, 48 MB: 57 %, 96 MB: 60 %, 200 MB: 63 %, one group for the whole block: 66 %.
+TILE_GROUP_BYTES = 4e9
 
 
 class _Level:

@@ -135,7 +135,8 @@ int eyoc_kernel_map_self(const int32_t* coords, int64_t n, const uint64_t* table
 int eyoc_kernel_map_transpose(const int32_t* nbr_down, int64_t n_coarse, int64_t n_fine, int K, int32_t* nbr_up,
                               eyoc_stream_t stream);
 /* Tile order for the tensor-core convolution: row_perm = output rows stably sorted by (cloud / group_clouds, bit mask
- * of the kernel offsets that have a neighbour), nbr_tiled[k, i] = nbr[k, row_perm[i]].  Rows with the same neighbour
+ * of the kernel offsets that have a neighbour - the offsets ordered by how many rows have them, the rarest in the most
+ * significant bit, ties by offset index), nbr_tiled[k, i] = nbr[k, row_perm[i]].  Rows with the same neighbour
  * pattern share 128-row tiles (dense or skipped (tile, offset) items) while each group of clouds stays contiguous
  * (L2 working set of the gather).  K <= 27; max_batch = largest batch index (sizes the sort key). */
 size_t eyoc_tile_order_workspace_bytes(int64_t n_out);

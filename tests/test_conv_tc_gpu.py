@@ -104,19 +104,30 @@ def test_tile_order_and_tiled_conv():
     from eyoc_b200 import nn as enn
     from eyoc_b200.sparse import CoordinateManager
     from tests.test_resunet_gpu import _cloud
+    from eyoc_b200 import sparse as sp
     coords = torch.from_numpy(_cloud(4000, 4, batch=6)).cuda()
-    mgr = CoordinateManager(coords)
-    nbr = mgr.kernel_map(1, 1, 3)
-    tiled, perm = mgr.tiled_map(1, 1, 3)
-    n = nbr.shape[1]
+    saved_budget = sp.TILE_GROUP_BYTES
+    try:
+        sp.TILE_GROUP_BYTES = 2.5e6                  # small budget: several cloud groups in this 6-cloud block
+        mgr = CoordinateManager(coords)
+        nbr = mgr.kernel_map(1, 1, 3)
+        tiled, perm = mgr.tiled_map(1, 1, 3)
+        n = nbr.shape[1]
+        rows_per_cloud = max(1, n // (mgr.max_batch + 1))
+        group = max(1, min(mgr.max_batch + 1, int(sp.TILE_GROUP_BYTES // (rows_per_cloud * 4 * 64))))
+    finally:
+        sp.TILE_GROUP_BYTES = saved_budget
+    assert mgr.max_batch == 5 and 1 <= group < 6
     assert torch.equal(torch.sort(perm.long())[0], torch.arange(n, device='cuda'))
     assert torch.equal(tiled, nbr[:, perm.long()])
-    mask = ((nbr >= 0).long() << torch.arange(27, device='cuda')[:, None]).sum(0)
-    rows_per_cloud = max(1, n // (mgr.max_batch + 1))
-    assert mgr.max_batch == 5
-    from eyoc_b200 import sparse as sp
-    group = max(1, min(mgr.max_batch + 1, int(sp.TILE_GROUP_BYTES // (rows_per_cloud * 4 * 64))))
-    key = ((coords[:, 0].long() // group) << 27) | mask
+    # sort key: (cloud group, neighbour mask with the offsets ordered by frequency - the rarest offset in the top bit,
+    # ties by offset index)
+    bits = (nbr >= 0).long()                                       # [27, n]
+    cnt = bits.sum(1).tolist()
+    order = sorted(range(27), key=lambda k: (cnt[k], k))
+    pos = {k: 26 - r for r, k in enumerate(order)}
+    pmask = sum(bits[k] << pos[k] for k in range(27))
+    key = ((coords[:, 0].long() // group) << 27) | pmask
     ks = key[perm.long()]
     assert bool((ks[1:] >= ks[:-1]).all())
     same = ks[1:] == ks[:-1]
