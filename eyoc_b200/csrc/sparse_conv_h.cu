@@ -493,8 +493,9 @@ sparse_conv_h_kernel(HArgs a) {
         // order: the accumulation order of a row stays fixed, results are deterministic) and the two threads' bookkeeping
         // overlaps the other one's MMAs.  A weight slab is released when every issuing thread is past it (a commit from a
         // thread that used the slab, a plain arrival from one that did not).
-        // Barrier waits cost ~250 cycles even when the phase is long complete, so the waits of the NEXT pair (its weight
-        // slab, this thread's item in it) are probed with non-blocking test_wait BEFORE the current item's MMAs are issued:
+        // Barrier waits cost ~250 cycles even when the phase is long complete, so the single issuer of the 128-channel
+        // kernel probes the waits of the NEXT pair (its weight slab, its item) with non-blocking test_wait BEFORE the
+        // current item's MMAs are issued:
         // the probes' latency hides behind the issue, and the blocking wait is only taken when a probe came back negative.
         // A probe looks one pair ahead at most, which keeps the parity test unambiguous (the stage's previous user lies
         // >= 3 pairs back, the other issuer is past it: see the static_assert above).
@@ -523,10 +524,10 @@ sparse_conv_h_kernel(HArgs a) {
                     if (tracing && i < 96) g_trace[tcta][i][3] = clock64();
                     if (!(pa_idx == i && pa_ok)) mbar_wait(a_full + 8 * (s * RB + n % RB), (n / RB) & 1u);
                     if (tracing && i < 96) g_trace[tcta][i][4] = clock64();
-                    fence_proxy_async();                 // the stage was written through the generic proxy (cp.async)
+                    if (!(ablate & 512)) fence_proxy_async();        // the stage was written through the generic proxy (cp.async)
                     tc_fence_after();
                     // ---- probes for the next pair
-                    {
+                    if (!PER_TILE && !(ablate & 256)) {        // measured: +8 % for the single issuer, -2 % for the two per-tile issuers
                         const int np = (i + 1 < nitems && !item_first(it_next)) ? i + 2 : i + 1;      // a pair has <= 2 items
                         int jj = -1;
                         uint32_t cj = 0;

@@ -48,7 +48,10 @@ def main():
             else:
                 enn.sparse_conv_raw(x, None, nbr, W, None, None, None, True, False, out, row_perm=perm, nbr_tiled=True, wt_img=img)
         M = int((nbr >= 0).sum())
-        for flags, name in ((0, 'full'), (6, 'MMA only'), (5, 'gather only'), (7, 'skeleton')):
+        variants = ((0, 'full'), (6, 'MMA only'), (5, 'gather only'), (7, 'skeleton'))
+        if h:
+            variants += ((32768, 'full (DBG build)'), (32768 | 256, 'DBG, no probes'), (32768 | 512, 'DBG, no proxy fence'), (32768 | 768, 'DBG, neither'))
+        for flags, name in variants:
             _C.check(set_ablate(flags))
             ts_ = []
             for _ in range(4):
