@@ -282,11 +282,11 @@ sparse_conv_h_kernel(HArgs a) {
         auto copy_item = [&](int i, const int (&idx)[NI]) {
             const uint32_t it = items[i];
             const uint32_t s = (uint32_t)(i % NXS), n = (uint32_t)(i / NXS);     // stage and which use of it this is
-            if (tracing && !(ablate & 128) && (warp % WPG) == 0 && lane == 0 && i < 96) g_trace[tcta][i][0] = clock64();
+            if (tracing && (warp % WPG) == 0 && lane == 0 && i < 96) g_trace[tcta][i][0] = clock64();
             // every lane waits (one warp-wide instruction): an elected-lane wait would leave the warp divergent for the
             // compiler, and each of the shuffles below would take its slow WARPSYNC path
             if (n > 0) mbar_wait(a_empty + 8 * (s * RB + (n - 1) % RB), ((n - 1) / RB) & 1u);    // the MMAs of its previous use have completed
-            if (tracing && !(ablate & 128) && (warp % WPG) == 0 && lane == 0 && i < 96) g_trace[tcta][i][1] = clock64();
+            if (tracing && (warp % WPG) == 0 && lane == 0 && i < 96) g_trace[tcta][i][1] = clock64();
             if (!(ablate & 2)) {
                 const int ci = item_c(it);
                 const bool first = ci < nch0;
@@ -302,7 +302,7 @@ sparse_conv_h_kernel(HArgs a) {
                 }
             }
             cp_async_arrive_noinc(a_full + 8 * (s * RB + n % RB));
-            if (tracing && !(ablate & 128) && (warp % WPG) == 0 && lane == 0 && i < 96) g_trace[tcta][i][2] = clock64();
+            if (tracing && (warp % WPG) == 0 && lane == 0 && i < 96) g_trace[tcta][i][2] = clock64();
         };
         // Output row of tile row `tid` of each tile, for the epilogue (loaded here so that its latency is long gone).
         int orow[NTILE];
@@ -553,14 +553,12 @@ sparse_conv_h_kernel(HArgs a) {
                     }
                     const uint32_t xs = sX + s * XS_BYTES;
                     uint32_t acc = (started >> t) & 1u;
-                    if (tracing && (ablate & 128) && i < 96) g_trace[tcta][i][0] = clock64();      // probes issued
                     if (!(ablate & 1)) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {                        // virtual channels: j = 0, 1 x_hi; j = 2, 3 x_lo'
                             umma_f16(d, make_desc_sw128(wh + j * 32), make_desc_sw128(xs + j * 32), IDESC, acc);
                             acc = 1u;
                         }
-                        if (tracing && (ablate & 128) && i < 96) g_trace[tcta][i][1] = clock64();  // MMAs issued
                         if (WIDE) {
 #pragma unroll
                             for (int j = 0; j < 2; ++j)                      // W_lo x_hi
@@ -575,7 +573,6 @@ sparse_conv_h_kernel(HArgs a) {
                     if (used) umma_commit(w_empty + 8 * ws);
                     else mbar_arrive(w_empty + 8 * ws);
                     ++w_it;
-                    if (tracing && (ablate & 128) && i < 96) g_trace[tcta][i][2] = clock64();      // slab released
                 }
                 it = it_next;
             }

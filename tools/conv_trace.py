@@ -55,12 +55,6 @@ def main():
             nit = int(tb[200 + cta, 5])
             t0 = tb[200 + cta, 0]
             print(f' CTA {200 + cta}: items {nit}; phases (prologue, main, drain, epilogue) = {np.diff(tb[200 + cta, :5])}')
-            if flags & 128:
-                print('  item  wait_start  +wait_done  +probes  +mmas  +commit  slab_released(abs)')
-                for i in range(min(nit, 40)):
-                    r = b[i]
-                    print(f'  {i:4d}  {r[3] - t0:10d}  {r[4] - r[3]:10d}  {r[0] - r[4]:7d}  {r[1] - r[0]:5d}  {r[5] - r[1]:7d}  {r[2] - t0:10d}')
-                continue
             print('  item  P.wait_start  P.wait_cycles  P.issued   M.wait_start  M.wait_cycles  M.issue_cycles')
             for i in range(min(nit, 40)):
                 r = b[i]
