@@ -435,20 +435,33 @@ knn_tc_kernel(const float* __restrict__ Q, const float* __restrict__ R, const ui
             const uint32_t dst = sQ + (uint32_t)p * 128u + (uint32_t)((c ^ (p & 7)) << 4);
             cp_async16_or_zero(dst, Qh + (size_t)max(min(q, nq - 1), 0) * ROWB + c * 16, q < nq ? 0 : -1);
         }
-        cp_async_arrive_noinc(q_full);
-        for (int tt = 0; tt < ntl; ++tt) {
-            const uint32_t s = (uint32_t)(tt % NS);
-            const int r0 = (tile0 + tt) * TRT;
-            mbar_wait(r_empty + 8 * s, ((uint32_t)(tt / NS) & 1u) ^ 1u);
-            const uint32_t base = sR + s * (uint32_t)(TRT * ROWB);
+        // Hand-over by the book: a thread's copies are complete (cp.async.wait_group) and made visible to the async proxy
+        // the MMA reads through (fence.proxy.async) BEFORE the thread arrives on the stage's barrier.  The wait is deferred
+        // by one tile so the copies of tile t + 1 are in flight while tile t lands.
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        fence_proxy_async();
+        mbar_arrive(q_full);
+        for (int tt = 0; tt <= ntl; ++tt) {
+            if (tt < ntl) {
+                const uint32_t s = (uint32_t)(tt % NS);
+                const int r0 = (tile0 + tt) * TRT;
+                mbar_wait(r_empty + 8 * s, ((uint32_t)(tt / NS) & 1u) ^ 1u);
+                const uint32_t base = sR + s * (uint32_t)(TRT * ROWB);
 #pragma unroll 8
-            for (int qq = 0; qq < 32; ++qq) {
-                const int p = w4 * 128 + qq * 4 + rsub;
-                const int j = r0 + p;
-                const uint32_t dst = base + (uint32_t)p * 128u + (uint32_t)((c ^ (p & 7)) << 4);
-                cp_async16_or_zero(dst, Rh + (size_t)min(j, nr - 1) * ROWB + c * 16, j < nr ? 0 : -1);
+                for (int qq = 0; qq < 32; ++qq) {
+                    const int p = w4 * 128 + qq * 4 + rsub;
+                    const int j = r0 + p;
+                    const uint32_t dst = base + (uint32_t)p * 128u + (uint32_t)((c ^ (p & 7)) << 4);
+                    cp_async16_or_zero(dst, Rh + (size_t)min(j, nr - 1) * ROWB + c * 16, j < nr ? 0 : -1);
+                }
             }
-            cp_async_arrive_noinc(r_full + 8 * s);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (tt > 0) {
+                asm volatile("cp.async.wait_group 1;" ::: "memory");      // tile tt - 1 has landed
+                fence_proxy_async();
+                mbar_arrive(r_full + 8 * (uint32_t)((tt - 1) % NS));
+            }
         }
     } else {
         // =========================================================== MMA issuer

@@ -96,10 +96,14 @@ struct HArgs {
     uint8_t* out; int out_packed;
     float acc_scale;                  // 2^-a: undoes the power-of-two weight pre-scale
     int K, n_out, cout, relu, l2norm, nbr_tiled;
+    int slot;                         // launch slot of the persistent grid's work counters
 };
 
 // Debug / measurement only (tools/conv_ablate.py): bit 0 = skip the MMAs, bit 1 = skip the gather copies, bit 2 = skip
 // the weight-slab copies, bit 3 = record per-CTA phase timestamps.  Results are garbage when bits 0-2 are set.
+// work distribution of the persistent grid: one counter per launch slot and 128-channel part, reset by the last CTA
+__device__ unsigned int g_next[64][2];
+__device__ unsigned int g_done[64];
 __device__ int g_ablate = 0;
 __device__ long long g_times[1024][6];
 // bit 4: CTAs 200..203 trace their first 96 items: [cta][item][0..2] the item's producer warp (empty wait start / end /
@@ -140,7 +144,7 @@ sparse_conv_h_kernel(HArgs a) {
     __shared__ uint32_t tmask[32];
     __shared__ uint16_t pair_off[27 * 12 + 1];
     __shared__ uint16_t items[MAX_ITEMS];
-    __shared__ int nitems_s;
+    __shared__ int nitems_s, nslabs_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long t_start = clock64();
@@ -153,8 +157,8 @@ sparse_conv_h_kernel(HArgs a) {
     const uint32_t w_full = smem_u32(&bars[2 * NXS * RB]), w_empty = smem_u32(&bars[2 * NXS * RB + NSW]);
     const uint32_t done_bar = smem_u32(&bars[2 * NXS * RB + 2 * NSW]);
     const int wload_warp = NPW, mma_warp = NPW + 1;
-    const int tile0 = blockIdx.x * NTILE;
     const int ntiles = (a.n_out + TR - 1) / TR;
+    const int nblocks = (ntiles + NTILE - 1) / NTILE;            // tile pairs of the launch
 
     if (tid == 0) {
         for (int i = 0; i < NXS * RB; ++i) { mbar_init(a_full + 8 * i, 32 * WPG); mbar_init(a_empty + 8 * i, 1); }
@@ -162,17 +166,33 @@ sparse_conv_h_kernel(HArgs a) {
         mbar_init(done_bar, NMMA);
         mbar_init_fence();
     }
+    if (warp == mma_warp) tmem_alloc(smem_u32(&tmem_base_s), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    // PERSISTENT: the grid is one CTA per SM (per 128-channel part); each CTA walks the tile pairs blockIdx.x,
+    // blockIdx.x + gridDim.x, ... - barriers, TMEM and the stage / slab rings are set up once and keep their phase across
+    // tile pairs (all ring positions are functions of the RUNNING item / slab counters ibase / wbase).  Between two CTAs of
+    // a non-persistent launch an SM idles ~10 % of a CTA's life (teardown, launch, TMEM allocation).
+    // Tile pairs are handed out by an atomic counter in launch order (what the hardware scheduler does for a plain grid):
+    // pairs differ a lot in their number of work items, so a static stride would leave SMs idle at the end.
+    uint32_t ibase = 0, wbase = 0, iter = 0;
+    __shared__ int pb_s;
+    for (;; ++iter) {
+    if (tid == 0) pb_s = (int)atomicAdd(&g_next[a.slot][blockIdx.y], 1u);
+    __syncthreads();
+    const int pb = pb_s;
+    if (pb >= nblocks) break;
+    const int tile0 = pb * NTILE;
     if (tid < NTILE) {
         uint32_t m = 0;
         if (a.nbr == nullptr) m = tile0 + tid < ntiles ? 1u : 0u;
         else if (a.tile_masks && tile0 + tid < ntiles) m = __ldg(a.tile_masks + tile0 + tid);
         valid[tid] = m;
     }
-    if (warp == mma_warp) tmem_alloc(smem_u32(&tmem_base_s), 512);
-    tc_fence_before();
     __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_base_s;
 
     // ---- which kernel offsets have a neighbour in each tile (only when the caller did not precompute the masks)
     if (a.nbr != nullptr && a.tile_masks == nullptr) {
@@ -207,10 +227,11 @@ sparse_conv_h_kernel(HArgs a) {
     __syncthreads();
     if (warp == 0) {
         const int npairs = a.K * nch;
-        int carry = 0;
+        int carry = 0, slabs = 0;
         for (int p0 = 0; p0 < npairs; p0 += 32) {
             const int p = p0 + lane;
             const int c = p < npairs ? __popc(tmask[p / nch]) : 0;
+            slabs += __popc(__ballot_sync(0xffffffffu, c > 0));
             int x = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -220,7 +241,7 @@ sparse_conv_h_kernel(HArgs a) {
             if (p < npairs) pair_off[p] = (uint16_t)(carry + x - c);
             carry += __shfl_sync(0xffffffffu, x, 31);
         }
-        if (lane == 0) nitems_s = carry;
+        if (lane == 0) { nitems_s = carry; nslabs_s = slabs; }
     }
     __syncthreads();
     for (int p = tid; p < a.K * nch; p += blockDim.x) {
@@ -237,11 +258,12 @@ sparse_conv_h_kernel(HArgs a) {
     }
     __syncthreads();
     const int nitems = nitems_s;
+    const int nslabs = nslabs_s;
     // the measurement hooks exist only in the DBG instantiation (launched while eyoc_debug_convh_ablate flags are set)
     const int ablate = DBG ? g_ablate : 0;
-    const bool timing = DBG && (ablate & 8) && tid == 0 && blockIdx.x < 1024 && blockIdx.y == 0;
-    const bool tracing = DBG && (ablate & 16) && blockIdx.x >= 200 && blockIdx.x < 204 && blockIdx.y == 0;
-    const int tcta = blockIdx.x - 200;
+    const bool timing = DBG && (ablate & 8) && tid == 0 && iter == 0 && blockIdx.x < 1024 && blockIdx.y == 0;
+    const bool tracing = DBG && (ablate & 16) && iter == 0 && blockIdx.x >= 100 && blockIdx.x < 104 && blockIdx.y == 0;
+    const int tcta = blockIdx.x - 100;
     if (timing) { g_times[blockIdx.x][0] = t_start; g_times[blockIdx.x][1] = clock64(); g_times[blockIdx.x][5] = nitems; }
 
     if (tid < NPT) {
@@ -281,7 +303,7 @@ sparse_conv_h_kernel(HArgs a) {
         // rows without a neighbour are zero-filled by the copy itself (source size 0)
         auto copy_item = [&](int i, const int (&idx)[NI]) {
             const uint32_t it = items[i];
-            const uint32_t s = (uint32_t)(i % NXS), n = (uint32_t)(i / NXS);     // stage and which use of it this is
+            const uint32_t s = (ibase + (uint32_t)i) % NXS, n = (ibase + (uint32_t)i) / NXS;     // stage and which use of it this is
             if (tracing && (warp % WPG) == 0 && lane == 0 && i < 96) g_trace[tcta][i][0] = clock64();
             // every lane waits (one warp-wide instruction): an elected-lane wait would leave the warp divergent for the
             // compiler, and each of the shuffles below would take its slow WARPSYNC path
@@ -331,7 +353,7 @@ sparse_conv_h_kernel(HArgs a) {
         }
         // =========================================================== epilogue: TMEM -> smem transpose -> global
         if (timing) g_times[blockIdx.x][2] = clock64();
-        mbar_wait(done_bar, 0);
+        mbar_wait(done_bar, iter & 1u);
         if (timing) g_times[blockIdx.x][3] = clock64();
         tc_fence_after();
         const int q4 = warp & 3;                 // TMEM lane quadrant this warp may read
@@ -470,7 +492,7 @@ sparse_conv_h_kernel(HArgs a) {
     } else if (warp == wload_warp) {
         // =========================================================== weight slabs: one TMA bulk copy each
         if (lane == 0) {
-            uint32_t w_it = 0;
+            uint32_t w_it = wbase;
             for (int i = 0; i < nitems; ++i) {
                 const uint32_t it = items[i];
                 if (!item_first(it)) continue;
@@ -501,7 +523,7 @@ sparse_conv_h_kernel(HArgs a) {
         // >= 3 pairs back, the other issuer is past it: see the static_assert above).
         const int t_own = warp - mma_warp;
         if (lane == 0 && t_own < NMMA) {
-            uint32_t w_it = 0, started = 0, ws = 0;
+            uint32_t w_it = wbase, started = 0, ws = 0;
             bool used = false;
             int pa_idx = -1;                  // item whose "full" barrier was probed / the probe's result
             uint32_t pa_ok = 0, pw_slab = 0xffffffffu, pw_ok = 0;
@@ -519,7 +541,7 @@ sparse_conv_h_kernel(HArgs a) {
                 if (!PER_TILE || t == t_own) {
                     used = true;
                     const uint32_t wh = sW + ws * W_BYTES;
-                    const uint32_t s = (uint32_t)(i % NXS), n = (uint32_t)(i / NXS);
+                    const uint32_t s = (ibase + (uint32_t)i) % NXS, n = (ibase + (uint32_t)i) / NXS;
                     const uint32_t d = tmem_base + (uint32_t)(t * TR);
                     if (tracing && i < 96) g_trace[tcta][i][3] = clock64();
                     if (!(pa_idx == i && pa_ok)) mbar_wait(a_full + 8 * (s * RB + n % RB), (n / RB) & 1u);
@@ -546,7 +568,7 @@ sparse_conv_h_kernel(HArgs a) {
                             pw_ok = mbar_test(w_full + 8 * ((w_it + 1) % NSW), ((w_it + 1) / NSW) & 1u);
                         }
                         if (jj >= 0) {
-                            const uint32_t sj = (uint32_t)(jj % NXS), nj = (uint32_t)(jj / NXS);
+                            const uint32_t sj = (ibase + (uint32_t)jj) % NXS, nj = (ibase + (uint32_t)jj) / NXS;
                             pa_idx = jj;
                             pa_ok = mbar_test(a_full + 8 * (sj * RB + nj % RB), (nj / RB) & 1u);
                         }
@@ -580,9 +602,22 @@ sparse_conv_h_kernel(HArgs a) {
         }
         __syncwarp();
     }
+    // end of this tile pair: the epilogue has drained the accumulators and released the stage memory it used
+    tc_fence_before();
     __syncthreads();
+    tc_fence_after();
+    ibase += (uint32_t)nitems;
+    wbase += (uint32_t)nslabs;
+    }   // persistent loop over tile pairs
+    if (tid == 0) {                                              // the last CTA of the launch re-arms the slot
+        const unsigned int d = atomicAdd(&g_done[a.slot], 1u);
+        if (d == gridDim.x * gridDim.y - 1) {
+            g_next[a.slot][0] = 0u;
+            g_next[a.slot][1] = 0u;
+            g_done[a.slot] = 0u;
+        }
+    }
     if (warp == mma_warp) {
-        tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
 }
@@ -676,8 +711,19 @@ int launch_h2(const HArgs& a, cudaStream_t stream) {
     const size_t smem = (size_t)NXS * XS_BYTES + (size_t)NSW * (WIDE ? 256 : 128) * 128;
     EYOC_CUDA(cudaFuncSetAttribute(sparse_conv_h_kernel<WIDE, NSW, NXS, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = (a.n_out + TR - 1) / TR;
-    dim3 grid((tiles + NTILE - 1) / NTILE, WIDE ? a.cout / 128 : 1);
-    sparse_conv_h_kernel<WIDE, NSW, NXS, DBG><<<grid, NPT + 96, smem, stream>>>(a);
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        EYOC_CUDA(cudaGetDevice(&dev));
+        EYOC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int parts = WIDE ? a.cout / 128 : 1;
+    const int nblocks = (tiles + NTILE - 1) / NTILE;
+    dim3 grid(min(nblocks, max(1, num_sms / parts)), parts);        // persistent: one CTA per SM
+    static unsigned int launch_seq = 0;
+    HArgs b = a;
+    b.slot = (int)(launch_seq++ % 64u);
+    sparse_conv_h_kernel<WIDE, NSW, NXS, DBG><<<grid, NPT + 96, smem, stream>>>(b);
     EYOC_LAUNCH_CHECK();
     return EYOC_OK;
 }

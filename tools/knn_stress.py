@@ -1,0 +1,25 @@
+import sys, torch
+sys.path.insert(0, '/root/repo')
+from eyoc_b200.lib import eval as ev
+g = torch.Generator().manual_seed(5)
+def _norm(x): return x / x.norm(dim=-1, keepdim=True)
+for n, form in ((5000, 0), (8000, 1)):
+    F0, F1 = _norm(torch.randn(n, 32, generator=g)).cuda(), _norm(torch.randn(n, 32, generator=g)).cuda()
+    ev.KNN_MODE = 'fp32'; ref = ev.knn1(F0, F1, form=form)
+    ev.KNN_MODE = 'tc'
+    bad = 0
+    for it in range(60):
+        got = ev.knn1(F0, F1, form=form)
+        d = int((got != ref).sum())
+        if d: bad += 1; print('form', form, 'iter', it, 'mismatches', d, (got != ref).nonzero().flatten()[:8].tolist())
+    print('form', form, 'n', n, 'bad runs', bad, 'of 60')
+# batched too
+F0, F1 = _norm(torch.randn(16, 8000, 32, generator=g)).cuda(), _norm(torch.randn(16, 8000, 32, generator=g)).cuda()
+ev.KNN_MODE = 'fp32'; ref = ev.knn1(F0, F1, form=1)
+ev.KNN_MODE = 'tc'
+bad = 0
+for it in range(20):
+    got = ev.knn1(F0, F1, form=1)
+    d = int((got != ref).sum())
+    if d: bad += 1; print('batched iter', it, 'mismatches', d)
+print('batched bad runs', bad, 'of 20')
