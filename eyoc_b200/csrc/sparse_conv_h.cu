@@ -19,8 +19,10 @@
 //     cp.async mainloop's hand-over; the proxy fence is issued by the MMA thread), so no producer ever waits on its own
 //     copies or on an index load (the next item's indices are prefetched into a second named register set);
 //   * the epilogue writes split-half rows again (or fp32 for the network output).
+//   * the grid is persistent: one CTA per SM, tile pairs handed out by an atomic counter, all rings keep their phase.
 // Work items, tile order, weight slabs by TMA bulk copy and the TMEM accumulator layout (2 tiles x 256 columns) are those
 // of the tf32 kernel.
+#include <atomic>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "../../include/eyoc_b200.h"
@@ -720,9 +722,9 @@ int launch_h2(const HArgs& a, cudaStream_t stream) {
     const int parts = WIDE ? a.cout / 128 : 1;
     const int nblocks = (tiles + NTILE - 1) / NTILE;
     dim3 grid(min(nblocks, max(1, num_sms / parts)), parts);        // persistent: one CTA per SM
-    static unsigned int launch_seq = 0;
+    static std::atomic<unsigned int> launch_seq{0};          // 64 counter slots: launches in flight never share one
     HArgs b = a;
-    b.slot = (int)(launch_seq++ % 64u);
+    b.slot = (int)(launch_seq.fetch_add(1u) % 64u);
     sparse_conv_h_kernel<WIDE, NSW, NXS, DBG><<<grid, NPT + 96, smem, stream>>>(b);
     EYOC_LAUNCH_CHECK();
     return EYOC_OK;
