@@ -205,6 +205,15 @@ int eyoc_debug_convh_times(long long* host_out_1024x6);
  * MMA thread: full-wait start, end, after commit}. */
 int eyoc_debug_convh_trace(long long* host_out_4x96x6);
 
+/* ---------------------------------------------------------------- robust linearised pose (validation path)
+ * util/transform_estimation.py:89-116 est_quad_linear_robust: `iterations` (reference: 20) rounds of a weighted small-angle
+ * 6-DoF solve from pts0 [n, 3] to pts1 [n, 3] with the reference's reweighting (w = par / (|r| + par), par halved every
+ * five rounds); weight [n] or NULL (ones).  trans_4x4 [16] row-major maps pts0 onto pts1.  One CTA; normal equations and
+ * the 6 x 6 solve in fp64. */
+size_t eyoc_irls_workspace_bytes(int64_t n);
+int eyoc_irls_pose(const float* pts0, const float* pts1, const float* weight, int64_t n, int iterations, float* trans_4x4,
+                   void* workspace, size_t workspace_bytes, eyoc_stream_t stream);
+
 /* ---------------------------------------------------------------- host-side index planning (no device work)
  * The six numpy draws the reference makes per pair on the global legacy RandomState (scripts/test_kitti.py:33-34,
  * :69-71 twice, scripts/SC2_PCR/SC2_PCR.py:288-289), restated on the raw MT19937 state (key[624], pos as returned by
