@@ -1,5 +1,8 @@
+"""Repeat the tensor-core pre-filtered 1-NN against the fp32-FMA kernel on the same data (single pair and batched): every run
+must return identical indices.  python tools/knn_stress.py"""
 import sys, torch
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from eyoc_b200.lib import eval as ev
 g = torch.Generator().manual_seed(5)
 def _norm(x): return x / x.norm(dim=-1, keepdim=True)
