@@ -330,6 +330,23 @@ def run_ours(args):
                 'share_of_step': tot_ms / ms if ms > 0 else None,
                 'algorithmic_bytes_per_step': tot_bytes // max(K, 1), 'achieved_tflops_fp32': tot_flops / (tot_ms / 1e3) / 1e12 if tot_ms > 0 else 0.0}
 
+    # ---- self-check outside the timed region: the estimator may be fed planted descriptors, so nothing above reads the
+    # network output of the 64-pair block.  Its rows must equal single-cloud forwards of the same clouds bit for bit
+    # (first, middle and last cloud of the block: the persistent conv grid makes ~45 trips per CTA at this size).
+    features_checked = True
+    with torch.no_grad():
+        from eyoc_b200.sparse import SparseTensor
+        Fblock = out['features']
+        offs = np.concatenate([[0], np.cumsum([n for pr in sizes for n in pr])])
+        for b in sorted({0, P, 2 * P - 1}):
+            cb = coords_d[offs[b]:offs[b + 1]].clone()
+            cb[:, 0] = 0
+            Fb = model(SparseTensor(torch.ones((len(cb), 1), device=dev), coordinates=cb)).F
+            same = torch.equal(Fblock[offs[b]:offs[b + 1]], Fb) and bool(torch.isfinite(Fb).all())
+            if not same:
+                features_checked = False
+                print(f'[rank {rank}] FEATURE SELF-CHECK FAILED for cloud {b}: max |diff| '
+                      f'{float((Fblock[offs[b]:offs[b + 1]] - Fb).abs().max())}', file=sys.stderr, flush=True)
     # ---- accuracy on this rank's block (vs ground truth; parity vs the oracle lives in tests/)
     Ts = out['trans'].cpu()
     rtes, rres, succ = [], [], 0
@@ -347,7 +364,7 @@ def run_ours(args):
                        'value_mode': 'coordinates, points and index plans resident in HBM', 'conv_mode': enn.CONV_MODE, 'tile_order': bool(enn.TILE_ORDER)},
             'e2e': {'value': e2e, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(coords_np.nbytes + xyz_np.nbytes + 2 * 8 * P * 8000 + 2 * 8 * P * 5000),
                     'd2h_bytes_per_step': int(rec_host.numel() * 4), 'ms_per_step': 1e3 * e2e_s / K},
-            'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
+            'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'features_checked': features_checked,
             'accuracy': {'rr_vs_gt': succ / P, 'rte_m_median': float(np.median(rtes)), 'rre_deg_median': float(np.nanmedian(rres))}}
     if world == 1 and not args.no_cpu_baseline:
         pps, dt, n, cores = run_cpu([0, 1, 2][:args.cpu_pairs + 1], warmup=1)
@@ -357,6 +374,8 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if not features_checked:
+        raise SystemExit('bench.py: the block forward differs from the single-cloud forward (see stderr)')
 
 
 def main():

@@ -98,14 +98,12 @@ struct HArgs {
     uint8_t* out; int out_packed;
     float acc_scale;                  // 2^-a: undoes the power-of-two weight pre-scale
     int K, n_out, cout, relu, l2norm, nbr_tiled;
-    int slot;                         // launch slot of the persistent grid's work counters
+    unsigned int* counters;           // [2] tile-pair hand-out counters of THIS launch (one per 128-channel part), zeroed
+                                      // on the launch stream by the host wrapper: launches never share a counter
 };
 
 // Debug / measurement only (tools/conv_ablate.py): bit 0 = skip the MMAs, bit 1 = skip the gather copies, bit 2 = skip
 // the weight-slab copies, bit 3 = record per-CTA phase timestamps.  Results are garbage when bits 0-2 are set.
-// work distribution of the persistent grid: one counter per launch slot and 128-channel part, reset by the last CTA
-__device__ unsigned int g_next[64][2];
-__device__ unsigned int g_done[64];
 __device__ int g_ablate = 0;
 __device__ long long g_times[1024][6];
 // bit 4: CTAs 200..203 trace their first 96 items: [cta][item][0..2] the item's producer warp (empty wait start / end /
@@ -183,7 +181,7 @@ sparse_conv_h_kernel(HArgs a) {
     uint32_t ibase = 0, wbase = 0, iter = 0;
     __shared__ int pb_s;
     for (;; ++iter) {
-    if (tid == 0) pb_s = (int)atomicAdd(&g_next[a.slot][blockIdx.y], 1u);
+    if (tid == 0) pb_s = (int)atomicAdd(a.counters + blockIdx.y, 1u);
     __syncthreads();
     const int pb = pb_s;
     if (pb >= nblocks) break;
@@ -611,14 +609,6 @@ sparse_conv_h_kernel(HArgs a) {
     ibase += (uint32_t)nitems;
     wbase += (uint32_t)nslabs;
     }   // persistent loop over tile pairs
-    if (tid == 0) {                                              // the last CTA of the launch re-arms the slot
-        const unsigned int d = atomicAdd(&g_done[a.slot], 1u);
-        if (d == gridDim.x * gridDim.y - 1) {
-            g_next[a.slot][0] = 0u;
-            g_next[a.slot][1] = 0u;
-            g_done[a.slot] = 0u;
-        }
-    }
     if (warp == mma_warp) {
         tmem_dealloc(tmem_base, 512);
     }
@@ -707,25 +697,29 @@ __global__ void tile_masks_kernel(const int* __restrict__ nbr, int K, int n_out,
 }
 
 int h_ablate = 0;      // host copy of g_ablate: non-zero selects the instrumented instantiation
+int h_grid_cap = 0;    // tests: cap on gridDim.x, so that small inputs walk many tile pairs per persistent CTA
 
 template <bool WIDE, int NSW, int NXS, bool DBG>
 int launch_h2(const HArgs& a, cudaStream_t stream) {
     const size_t smem = (size_t)NXS * XS_BYTES + (size_t)NSW * (WIDE ? 256 : 128) * 128;
     EYOC_CUDA(cudaFuncSetAttribute(sparse_conv_h_kernel<WIDE, NSW, NXS, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = (a.n_out + TR - 1) / TR;
-    static int num_sms = 0;
+    static std::atomic<int> sms_of[64];                     // SM count per device ordinal (0 = not queried yet)
+    int dev = 0;
+    EYOC_CUDA(cudaGetDevice(&dev));
+    int num_sms = dev < 64 ? sms_of[dev].load(std::memory_order_relaxed) : 0;
     if (num_sms == 0) {
-        int dev = 0;
-        EYOC_CUDA(cudaGetDevice(&dev));
         EYOC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        if (dev < 64) sms_of[dev].store(num_sms, std::memory_order_relaxed);
     }
     const int parts = WIDE ? a.cout / 128 : 1;
     const int nblocks = (tiles + NTILE - 1) / NTILE;
-    dim3 grid(min(nblocks, max(1, num_sms / parts)), parts);        // persistent: one CTA per SM
-    static std::atomic<unsigned int> launch_seq{0};          // 64 counter slots: launches in flight never share one
-    HArgs b = a;
-    b.slot = (int)(launch_seq.fetch_add(1u) % 64u);
-    sparse_conv_h_kernel<WIDE, NSW, NXS, DBG><<<grid, NPT + 96, smem, stream>>>(b);
+    int gx = min(nblocks, max(1, num_sms / parts));                  // persistent: one CTA per SM
+    if (h_grid_cap > 0) gx = min(gx, h_grid_cap);
+    dim3 grid(gx, parts);
+    // the launch's own hand-out counters, cleared in stream order: nothing is shared between launches in flight
+    EYOC_CUDA(cudaMemsetAsync(a.counters, 0, 2 * sizeof(unsigned int), stream));
+    sparse_conv_h_kernel<WIDE, NSW, NXS, DBG><<<grid, NPT + 96, smem, stream>>>(a);
     EYOC_LAUNCH_CHECK();
     return EYOC_OK;
 }
@@ -739,6 +733,11 @@ int launch_h(const HArgs& a, cudaStream_t stream) {
 extern "C" int eyoc_debug_convh_ablate(int flags) {
     h_ablate = flags;
     EYOC_CUDA(cudaMemcpyToSymbol(g_ablate, &flags, sizeof(int)));
+    return EYOC_OK;
+}
+
+extern "C" int eyoc_debug_convh_grid_cap(int max_ctas) {
+    h_grid_cap = max_ctas > 0 ? max_ctas : 0;
     return EYOC_OK;
 }
 
@@ -807,8 +806,8 @@ extern "C" int eyoc_sparse_conv_h(const void* in0, int c0, const void* in1, int 
                                   const int32_t* row_perm, int nbr_tiled, const uint32_t* tile_masks, const void* wt_img,
                                   float acc_scale, const float* scale, const float* shift, const void* residual,
                                   int residual_packed, int relu, int l2norm, void* out, int out_packed, int cout,
-                                  cudaStream_t stream) {
-    EYOC_CHECK_ARG(in0 && wt_img && out, "eyoc_sparse_conv_h: null argument");
+                                  uint32_t* counters, cudaStream_t stream) {
+    EYOC_CHECK_ARG(in0 && wt_img && out && counters, "eyoc_sparse_conv_h: null argument");
     EYOC_CHECK_ARG((in1 != nullptr) == (c1 > 0), "eyoc_sparse_conv_h: in1 and c1 must be given together");
     EYOC_CHECK_ARG(nbr || K == 1, "eyoc_sparse_conv_h: a neighbour table is required when K > 1");
     EYOC_CHECK_ARG(eyoc_sparse_conv_h_supported(c0, c1, cout, K, l2norm), "eyoc_sparse_conv_h: unsupported shape c0=%d c1=%d cout=%d K=%d", c0, c1, cout, K);
@@ -820,7 +819,7 @@ extern "C" int eyoc_sparse_conv_h(const void* in0, int c0, const void* in1, int 
     if (n_out == 0) return EYOC_OK;
     HArgs a{(const uint8_t*)in0, c0, (const uint8_t*)in1, c1, nbr, row_perm, tile_masks, (const __half*)wt_img, scale, shift,
             (const uint8_t*)residual, residual_packed, (uint8_t*)out, out_packed, acc_scale, K, (int)n_out, cout, relu, l2norm,
-            nbr_tiled};
+            nbr_tiled, counters};
     if (cout <= 64) return launch_h<false, 2, 6>(a, stream);       // 6 x 32 KB X stages + 2 x 16 KB weight slabs
     return launch_h<true, 2, 5>(a, stream);                          // 5 x 32 KB X stages + 2 x 32 KB weight slabs
 }

@@ -166,6 +166,7 @@ def sparse_conv_h_raw(in0, in1, nbr, weight, scale, shift, residual, relu, l2nor
     if weight.shape[-2] != c0 + c1:
         raise RuntimeError(f'kernel expects {weight.shape[-2]} input channels, got {c0}+{c1}')
     img, acc_scale = h_img if h_img is not None else split_weights_h(weight)
+    counters = torch.empty(2, dtype=torch.int32, device=in0.device)      # this launch's hand-out counters (zeroed by the library)
     ev = None
     if PROFILE is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -176,7 +177,7 @@ def sparse_conv_h_raw(in0, in1, nbr, weight, scale, shift, residual, relu, l2nor
             _C.ptr(row_perm), _C.c_int(int(nbr_tiled)), _C.ptr(tile_masks), _C.ptr(img), _C.c_float(acc_scale), _C.ptr(scale),
             _C.ptr(shift), _C.ptr(residual), _C.c_int(int(residual is not None and residual.dtype == torch.float16)),
             _C.c_int(int(relu)), _C.c_int(int(l2norm)), _C.ptr(out), _C.c_int(int(out.dtype == torch.float16)), _C.c_int(cout),
-            _C.stream()))
+            _C.ptr(counters), _C.stream()))
     if ev is not None:
         ev[1].record()
         PROFILE.append((ev[0], ev[1], dict(K=K, cin=c0 + c1, cout=cout, n_out=out.shape[0], nbr=nbr,

@@ -187,6 +187,8 @@ int eyoc_sparse_conv_tc(const float* in0, int c0, const float* in1, int c1, cons
  * Weights: wt_img = eyoc_convh_split_weights(weight * wscale) with wscale a power of two chosen by the caller so that
  * max |w| * wscale lies in [2^13, 2^14); acc_scale = 1 / wscale undoes it (exactly) in the epilogue.
  * tile_masks [ceil(n_out / 256)] (eyoc_tile_masks of the tiled table) or NULL (each CTA then derives its own).
+ * counters: 8 bytes of caller-owned device scratch PER LAUNCH (the persistent grid's tile-pair hand-out counters; cleared
+ * here in stream order, so concurrent launches on any number of streams never share state).
  * Supported shapes as reported by eyoc_sparse_conv_h_supported (those of the tf32 path). */
 size_t eyoc_convh_weight_image_halves(int K, int cin, int cout);
 int eyoc_convh_split_weights(const float* weight, int K, int cin, int cout, float wscale, void* wt_img, eyoc_stream_t stream);
@@ -197,7 +199,9 @@ int eyoc_sparse_conv_h_supported(int c0, int c1, int cout, int K, int l2norm);
 int eyoc_sparse_conv_h(const void* in0, int c0, const void* in1, int c1, const int32_t* nbr, int K, int64_t n_out,
                        const int32_t* row_perm, int nbr_tiled, const uint32_t* tile_masks, const void* wt_img,
                        float acc_scale, const float* scale, const float* shift, const void* residual, int residual_packed,
-                       int relu, int l2norm, void* out, int out_packed, int cout, eyoc_stream_t stream);
+                       int relu, int l2norm, void* out, int out_packed, int cout, uint32_t* counters, eyoc_stream_t stream);
+/* Test aid: cap gridDim.x of the persistent grid (0 = one CTA per SM), so that small inputs walk many tile pairs per CTA. */
+int eyoc_debug_convh_grid_cap(int max_ctas);
 /* Measurement aids of the split-half kernel, as eyoc_debug_conv_ablate / eyoc_debug_conv_times above. */
 int eyoc_debug_convh_ablate(int flags);
 int eyoc_debug_convh_times(long long* host_out_1024x6);
