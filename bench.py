@@ -108,6 +108,7 @@ def cpu_state_dict(seed=0):
 
 
 def run_cpu(pair_ids, warmup=0):
+    """-> (pairs/s from the MEDIAN per-pair time, total seconds, pairs timed, threads, per-pair seconds)."""
     import numpy as np
     import torch
     from eyoc_b200 import synth
@@ -118,12 +119,14 @@ def run_cpu(pair_ids, warmup=0):
     np.random.seed(0)
     for p in pairs[:warmup]:
         cpu_pair(p, sd)
-    t0 = time.perf_counter()
+    per = []
     for p in pairs[warmup:]:
+        t0 = time.perf_counter()
         cpu_pair(p, sd)
-    dt = time.perf_counter() - t0
-    n = len(pairs) - warmup
-    return n / dt, dt, n, cores
+        per.append(time.perf_counter() - t0)
+    n = len(per)
+    med = sorted(per)[n // 2] if n % 2 else 0.5 * (sorted(per)[n // 2 - 1] + sorted(per)[n // 2])
+    return 1.0 / med, sum(per), n, cores, per
 
 
 def run_reference(args):
@@ -132,11 +135,14 @@ def run_reference(args):
         return
     K, W = args.steps, args.warmup
     ids = list(range(W + K))
-    pps, dt, n, cores = run_cpu(ids, warmup=W)
-    sample = f'{n} timed pairs (1 pair per step) after {W} warm-up pairs; oracle port of the reference path, torch-CPU fp32'
+    pps_med, dt, n, cores, per = run_cpu(ids, warmup=W)
+    pps = n / dt                                   # the K timed steps as a whole, like the GPU arm
+    sample = (f'{n} timed pairs (1 pair per step) after {W} warm-up pairs, median {1e3 * sorted(per)[n // 2]:.0f} ms per pair; oracle port '
+              'of the reference path, torch-CPU fp32; weighted Kabsch of post_refinement without the dense diag_embed '
+              '(dense_weight=False: the reference builds a 256 MB [n, n] weight matrix there, common.py:33; the port is faster)')
     line = {'impl': 'reference', 'metric': 'point-cloud pairs/sec', 'value': pps, 'unit': 'pairs/s', 'n_gpus': args.gpus, 'steps': K,
             'warmup': W, 'ms_per_step': 1e3 * dt / max(n, 1), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': WORKLOAD, 'pairs_per_step': 1},
+            'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': WORKLOAD, 'pairs_per_step': 1, 'dense_weight': False},
             'cpu_baseline': {'value': pps, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': pps, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(line), flush=True)
@@ -347,6 +353,24 @@ def run_ours(args):
                 features_checked = False
                 print(f'[rank {rank}] FEATURE SELF-CHECK FAILED for cloud {b}: max |diff| '
                       f'{float((Fblock[offs[b]:offs[b + 1]] - Fb).abs().max())}', file=sys.stderr, flush=True)
+    # ---- SURVEY 8e parity: the gathered table at world N must be byte-identical to what ONE GPU computes for all N blocks
+    gather_checked = None
+    if world > 1 and not args.no_check_gather:
+        if rank == 0:
+            gather_checked = True
+            table = allrec.cpu()
+            for r in range(world):
+                prs = synth.make_pairs(list(range(r * P, r * P + P)))
+                c_np, x_np, d_np, sz = synth.collate_pairs(prs)
+                np.random.seed(1000 + r)
+                pl = plan_to_device(pipe.plan(sz), dev)
+                o = pipe.run(torch.from_numpy(c_np).to(dev), torch.from_numpy(x_np).to(dev), sz, plan=pl,
+                             descriptors=torch.from_numpy(d_np).to(dev) if desc_d is not None else None)
+                mine = pipe.records(o, list(range(r * P, r * P + P))).cpu()
+                if not torch.equal(mine.view(torch.int32), table[r * P:(r + 1) * P].view(torch.int32)):
+                    gather_checked = False
+                    print(f'[rank 0] GATHER CHECK FAILED for the block of rank {r}', file=sys.stderr, flush=True)
+        barrier()
     # ---- accuracy on this rank's block (vs ground truth; parity vs the oracle lives in tests/)
     Ts = out['trans'].cpu()
     rtes, rres, succ = [], [], 0
@@ -365,17 +389,22 @@ def run_ours(args):
             'e2e': {'value': e2e, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(coords_np.nbytes + xyz_np.nbytes + 2 * 8 * P * 8000 + 2 * 8 * P * 5000),
                     'd2h_bytes_per_step': int(rec_host.numel() * 4), 'ms_per_step': 1e3 * e2e_s / K},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'features_checked': features_checked,
+            'gather_checked': gather_checked,
             'accuracy': {'rr_vs_gt': succ / P, 'rte_m_median': float(np.median(rtes)), 'rre_deg_median': float(np.nanmedian(rres))}}
     if world == 1 and not args.no_cpu_baseline:
-        pps, dt, n, cores = run_cpu([0, 1, 2][:args.cpu_pairs + 1], warmup=1)
-        line['cpu_baseline'] = {'value': pps, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
-                                'sample': f'{n} pairs of the same generator after 1 warm-up pair ({dt:.1f} s); oracle port of the reference path (ME-algorithm restatement + SC2_PCR restatement), torch-CPU fp32'}
+        pps, dt, n, cores, per = run_cpu(list(range(args.cpu_pairs + 1)), warmup=1)
+        line['cpu_baseline'] = {'value': pps, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port', 'dense_weight': False,
+                                'sample': f'median of {n} pairs of the same generator after 1 warm-up pair ({dt:.1f} s in all, per pair '
+                                          + ' '.join(f'{x:.2f}' for x in per) + ' s); oracle port of the reference path (ME-algorithm '
+                                          'restatement + SC2_PCR restatement, dense_weight=False), torch-CPU fp32'}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     if not features_checked:
         raise SystemExit('bench.py: the block forward differs from the single-cloud forward (see stderr)')
+    if gather_checked is False:
+        raise SystemExit('bench.py: the gathered record table differs from the single-GPU table (see stderr)')
 
 
 def main():
@@ -387,8 +416,10 @@ def main():
     ap.add_argument('--pairs-per-gpu', type=int, default=64)
     ap.add_argument('--descriptors', default='planted', choices=['planted', 'network'])
     ap.add_argument('--conv-mode', default=None, choices=['fp32', 'tf32x3', 'f16x3'])
-    ap.add_argument('--cpu-pairs', type=int, default=2)
+    ap.add_argument('--cpu-pairs', type=int, default=5)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-check-gather', action='store_true',
+                    help='skip the world > 1 self-check (rank 0 recomputes every rank\'s block and compares the gathered table byte for byte)')
     ap.add_argument('--conv-breakdown', action='store_true')
     ap.add_argument('--no-tile-order', action='store_true')
     ap.add_argument('--tile-group-mb', type=float, default=None, help='L2 budget of one cloud group of the tile order (sparse.TILE_GROUP_BYTES)')

@@ -25,7 +25,7 @@ class SC2Cfg(ctypes.Structure):
 
 class SC2Hooks(ctypes.Structure):
     """struct eyoc_sc2_hooks."""
-    _fields_ = [('confidence', c_void_p), ('seeds', c_void_p), ('initial_trans', c_void_p)]
+    _fields_ = [('confidence', c_void_p), ('seeds', c_void_p), ('initial_trans', c_void_p), ('sc2_dense', c_void_p)]
 
 
 class SC2Layout(ctypes.Structure):
@@ -34,7 +34,7 @@ class SC2Layout(ctypes.Structure):
                                         'topk1', 'topk2', 'local_v', 'seed_weights', 'seed_trans', 'counters',
                                         'global_iters', 'local_notclose', 'best_seed', 'refine_counts', 'total',
                                         'csr_rowptr', 'csr_cols', 'csr_vals', 'csr_capacity', 'sort_keys', 'sort_idx',
-                                        'sort_offsets', 'sort_temp', 'sort_temp_bytes')] + \
+                                        'sort_offsets', 'sort_temp', 'sort_temp_bytes', 'near_bits', 'status')] + \
                [(k, c_int) for k in ('words_per_row', 'k1', 'k2', 'num_seeds')]
 
 
@@ -55,7 +55,8 @@ def lib():
         _lib.eyoc_launch_count.restype = ctypes.c_ulonglong
         for name in ('eyoc_knn1_workspace_bytes', 'eyoc_sc2pcr_workspace_bytes', 'eyoc_downsample_workspace_bytes',
                      'eyoc_tile_order_workspace_bytes', 'eyoc_conv_weight_image_floats', 'eyoc_voxelize_workspace_bytes',
-                     'eyoc_convh_weight_image_halves', 'eyoc_knn1_tc_workspace_bytes'):
+                     'eyoc_convh_weight_image_halves', 'eyoc_knn1_tc_workspace_bytes', 'eyoc_pick_seeds_workspace_bytes',
+                     'eyoc_power_iteration_workspace_bytes', 'eyoc_irls_workspace_bytes', 'eyoc_knn2_workspace_bytes'):
             if hasattr(_lib, name):
                 getattr(_lib, name).restype = c_size_t
     return _lib

@@ -409,7 +409,9 @@ knn_tc_kernel(const float* __restrict__ Q, const float* __restrict__ R, const ui
 #pragma unroll
                 for (int i = 1; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(v[i]));
                 runmax = fmaxf(runmax, cm);
-                const float th = runmax - tau;
+                // form 1: a product > 1 makes sqrt(2 - 2 s + 1e-6) NaN, and torch.argmin returns the FIRST NaN column
+                // whatever its s: every column whose score can exceed 1 is queued, not only those near the row maximum
+                const float th = (FORM == 1 ? fminf(runmax, 1.0f) : runmax) - tau;
                 if (live && cm >= th) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i)

@@ -53,17 +53,43 @@ __device__ __forceinline__ float cross_dist(const Pt& a, const Pt& b) {
 }
 
 // ------------------------------------------------------------------------------- first-order bit rows
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// 32 x 32 bit-matrix transpose across the lanes of a warp: lane r holds row r (bit c = M[r][c]) and receives column r
+// (bit c = M[c][r]).  Five exchange stages instead of one ballot per column.
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const uint32_t m = s == 16 ? 0x0000ffffu : s == 8 ? 0x00ff00ffu : s == 4 ? 0x0f0f0f0fu : s == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, s);
+        x = (lane & s) ? ((x & ~m) | ((y & ~m) >> s)) : ((x & m) | ((y & m) << s));
+    }
+    return x;
+}
+
 // grid (ceil(n/32), batch); lane = row, the 8 warps split the 32-bit words of each 1024-column tile.
 // cross_dist(i, j) == cross_dist(j, i) bit for bit ((a-b)^2 == (b-a)^2), so only the 32x32 bit blocks on and above the
-// diagonal are evaluated; the mirrored block is the bit transpose, assembled with one warp ballot per column.
+// diagonal are evaluated; the mirrored block is the bit transpose (shuffle butterfly).
+// Three bit matrices: hard (cross < d), tight (cross < d/2), near (||s_i - s_j|| < R, the NMS neighbourhood of pick_seeds,
+// SC2_PCR.py:50: "dist >= R" <=> "sum of squares >= s0", see sqrt_threshold).
+// The two correctly rounded square roots of cross_dist are only needed near a threshold: MUFU approximations (relative
+// error <= 2^-23, PTX ISA) first, and the exact evaluation for the whole warp step only when some lane's approximate value
+// lies within the error margin of d or d/2.  The margin 2^-20 (ds + dt) is > 4x the worst-case difference between the
+// approximate and the exactly rounded |ds - dt| ((2^-23 + 2^-24)(ds + dt) + 2^-24 |ds - dt|), so the bits are those of the
+// exact evaluation (tests/test_sc2pcr_gpu.py::test_first_order_bits_bit_exact).
 __global__ void __launch_bounds__(256)
-first_order_bits_kernel(const Pt* __restrict__ P, int n, int W, float d_thre, float d_half,
-                        uint32_t* __restrict__ hard, uint32_t* __restrict__ tight) {
+first_order_bits_kernel(const Pt* __restrict__ P, int n, int W, float d_thre, float d_half, float near_s0,
+                        uint32_t* __restrict__ hard, uint32_t* __restrict__ tight, uint32_t* __restrict__ near) {
     __shared__ Pt tile[CT];
     const int b = blockIdx.y;
     P += (size_t)b * n;
     hard += (size_t)b * n * W;
     tight += (size_t)b * n * W;
+    near += (size_t)b * n * W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int I = blockIdx.x;                        // 32-row block == word index of these rows
     const int i = I * 32 + lane;
@@ -77,26 +103,42 @@ first_order_bits_kernel(const Pt* __restrict__ P, int n, int W, float d_thre, fl
             const int J = (c0 >> 5) + wl;            // word (32-column block) index
             if (J * 32 >= n) break;
             if (J < I) continue;                      // below the diagonal: written by the mirrored block
-            uint32_t hb = 0, tb = 0, mh = 0, mt = 0;
+            uint32_t hb = 0, tb = 0, nb = 0;
 #pragma unroll 4
             for (int bit = 0; bit < 32; ++bit) {
                 const int j = J * 32 + bit;
-                const float c = cross_dist(me, tile[wl * 32 + bit]);
+                const Pt q = tile[wl * 32 + bit];
+                float dx = __fsub_rn(me.sx, q.sx), dy = __fsub_rn(me.sy, q.sy), dz = __fsub_rn(me.sz, q.sz);
+                const float ss = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));      // dist3_fma's sum of squares
+                dx = __fsub_rn(me.tx, q.tx); dy = __fsub_rn(me.ty, q.ty); dz = __fsub_rn(me.tz, q.tz);
+                const float tt = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                const float da = sqrt_approx(ss), db = sqrt_approx(tt);
+                const float ca = fabsf(da - db), mg = (da + db) * 9.5367431640625e-07f;      // 2^-20
+                bool h = ca < d_thre, t = ca < d_half;
+                const bool unsure = !(fabsf(ca - d_thre) > mg) || !(fabsf(ca - d_half) > mg);   // also true for NaN / Inf
+                if (__any_sync(0xffffffffu, unsure)) {
+                    const float c = fabsf(__fsub_rn(__fsqrt_rn(ss), __fsqrt_rn(tt)));
+                    h = c < d_thre;
+                    t = c < d_half;
+                }
                 const bool ok = row_ok && j < n;
-                const bool h = ok && c < d_thre, t = ok && c < d_half;
-                hb |= (uint32_t)h << bit;
-                tb |= (uint32_t)t << bit;
-                const uint32_t bh = __ballot_sync(0xffffffffu, h), bt = __ballot_sync(0xffffffffu, t);
-                if (lane == bit) { mh = bh; mt = bt; }    // row J*32+bit, columns I*32 .. I*32+31
+                hb |= (uint32_t)(ok && h) << bit;
+                tb |= (uint32_t)(ok && t) << bit;
+                nb |= (uint32_t)(ok && !(ss >= near_s0)) << bit;
             }
             if (row_ok) {
                 hard[(size_t)i * W + J] = hb;
                 tight[(size_t)i * W + J] = tb;
+                near[(size_t)i * W + J] = nb;
             }
-            const int jrow = J * 32 + lane;
-            if (J != I && jrow < n) {
-                hard[(size_t)jrow * W + I] = mh;
-                tight[(size_t)jrow * W + I] = mt;
+            if (J != I) {                             // warp-uniform
+                const uint32_t mh = transpose32(hb, lane), mt = transpose32(tb, lane), mn = transpose32(nb, lane);
+                const int jrow = J * 32 + lane;       // row J*32+lane, columns I*32 .. I*32+31
+                if (jrow < n) {
+                    hard[(size_t)jrow * W + I] = mh;
+                    tight[(size_t)jrow * W + I] = mt;
+                    near[(size_t)jrow * W + I] = mn;
+                }
             }
         }
     }
@@ -311,41 +353,43 @@ power_step_kernel(const Pt* __restrict__ P, const uint32_t* __restrict__ hard, i
 }
 
 // ------------------------------------------------------------------------------------------- pick_seeds
-// SC2_PCR.py:47-51: i survives iff for all j: score_i >= score_j or ||s_i - s_j|| >= R.
+// SC2_PCR.py:47-51: i survives iff for all j: score_i >= score_j or ||s_i - s_j|| >= R.  The neighbourhood test is the
+// `near` bit row written by first_order_bits_kernel, so this is a sparse scan: warp per row, grid (ceil(n / 8), batch).
 __global__ void __launch_bounds__(256)
-nms_kernel(const Pt* __restrict__ P, const float* __restrict__ conf, int n, float s0, float* __restrict__ scores) {
-    __shared__ float4 tile[CT];   // (sx, sy, sz, conf)
-    __shared__ int sup[32];
-    const int b = blockIdx.y;
-    P += (size_t)b * n;
+nms_bits_kernel(const uint32_t* __restrict__ near, const float* __restrict__ conf, int n, int W, float* __restrict__ scores) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n) return;
     conf += (size_t)b * n;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i = blockIdx.x * 32 + lane;
-    const Pt me = load_pt(P + min(i, n - 1));
-    const float ci = conf[min(i, n - 1)];
-    if (threadIdx.x < 32) sup[threadIdx.x] = 0;
+    const uint32_t* row = near + ((size_t)b * n + i) * W;
+    const float ci = conf[i];
     int suppressed = 0;
-    for (int c0 = 0; c0 < n; c0 += CT) {
-        __syncthreads();
-        for (int t = threadIdx.x; t < CT; t += 256) {
-            const int j = min(c0 + t, n - 1);
-            const float4 a = __ldg(reinterpret_cast<const float4*>(P + j));
-            tile[t] = make_float4(a.x, a.y, a.z, conf[j]);
-        }
-        __syncthreads();
-        const int lim = min(CT, n - c0);
-        for (int t = warp; t < lim; t += 8) {
-            // dist >= R  <=>  (sum of squares) >= s0: sqrt_rn is monotonic and s0 is the smallest fp32 whose correctly
-            // rounded root reaches R (sqrt_threshold on the host), so the root itself is never formed here
-            const float4 q = tile[t];
-            const float dx = __fsub_rn(me.sx, q.x), dy = __fsub_rn(me.sy, q.y), dz = __fsub_rn(me.sz, q.z);
-            const float ss = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-            suppressed |= (!(ci >= q.w)) && (!(ss >= s0));
+    for (int w = lane; w < W; w += 32) {
+        uint32_t m = __ldg(row + w);
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            suppressed |= !(ci >= conf[w * 32 + bit]);
         }
     }
-    if (suppressed) atomicOr(&sup[lane], 1);
-    __syncthreads();
-    if (warp == 0 && i < n) scores[(size_t)b * n + i] = sup[lane] ? __fmul_rn(ci, 0.0f) : ci;
+    suppressed = __any_sync(0xffffffffu, suppressed);
+    if (lane == 0) scores[(size_t)b * n + i] = suppressed ? __fmul_rn(ci, 0.0f) : ci;
+}
+
+// The same rule on a caller-supplied dense distance matrix (drop-in Matcher.pick_seeds(dists, scores, R, max_num)):
+// warp per row, coalesced row read.
+__global__ void __launch_bounds__(256)
+nms_dense_kernel(const float* __restrict__ dists, const float* __restrict__ conf, int n, float R, float* __restrict__ scores) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    conf += (size_t)b * n;
+    const float* row = dists + ((size_t)b * n + i) * n;
+    const float ci = conf[i];
+    int suppressed = 0;
+    for (int j = lane; j < n; j += 32) suppressed |= (!(ci >= conf[j])) && (!(__ldg(row + j) >= R));
+    suppressed = __any_sync(0xffffffffu, suppressed);
+    if (lane == 0) scores[(size_t)b * n + i] = suppressed ? __fmul_rn(ci, 0.0f) : ci;
 }
 
 // SC2_PCR.py:53-57 argsort(descending) -> first S: a stable segmented radix sort (descending value, ties keep the
@@ -373,6 +417,8 @@ struct SeedArgs {
     const uint32_t* hard;
     const uint32_t* tight;
     const int32_t* seeds;
+    const float* sc2_dense;   // hook: caller's dense SC2 rows [batch, S, n] (drop-in Matcher.cal_seed_trans), or null
+    int* status;              // bit 0: a dense SC2 value is not an integer in [0, 65535]
     int n, W, S, k1, k2, num_iterations;
     float d_thre, d_sq;
     int32_t* topk1;       // [batch, S, k1]
@@ -389,7 +435,9 @@ seed_consensus_kernel(SeedArgs a) {
     uint32_t* hrow = sm + W;             // [W]
     uint32_t* nzmap = sm + 2 * W;        // [W] columns with a non-zero SC2 value
     uint32_t* keys = sm + 3 * W;         // [n]  (count << 16) | (65535 - j)
-    __shared__ int ncand;
+    __shared__ int ncand, nnz, nwin;
+    __shared__ unsigned int hist[256], wtot[8], sel_bin, sel_rem;
+    __shared__ uint32_t win[MAXK];
     __shared__ int idx1[MAXK], idx2[MAXK], fine[MAXK], lval[MAXK];
     __shared__ uint32_t lhard[MAXK];
     __shared__ float ls[MAXK][3], lt[MAXK][3];
@@ -397,72 +445,128 @@ seed_consensus_kernel(SeedArgs a) {
 
     const int b = blockIdx.y, s = blockIdx.x;
     const Pt* P = a.P + (size_t)b * n;
-    const uint32_t* tight = a.tight + (size_t)b * n * W;
-    const int seed = a.seeds[(size_t)b * a.S + s];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k1 = a.k1, k2 = a.k2;
 
-    if (tid == 0) ncand = 0;
-    for (int w = tid; w < W; w += 256) {
-        trow[w] = tight[(size_t)seed * W + w];
-        hrow[w] = a.hard[((size_t)b * n + seed) * W + w];
-        nzmap[w] = 0;
-    }
+    if (tid == 0) { ncand = 0; nnz = 0; nwin = 0; }
+    for (int w = tid; w < W; w += 256) nzmap[w] = 0;
     __syncthreads();
-    // 1. compact the columns where hard[seed] is set
-    for (int w = tid; w < W; w += 256) {
-        uint32_t m = hrow[w];
-        const int c = __popc(m);
-        if (c) {
-            int pos = atomicAdd(&ncand, c);
-            while (m) {
-                const int bit = __ffs(m) - 1;
-                m &= m - 1;
-                keys[pos++] = 65535u - (uint32_t)(w * 32 + bit);
+    int nc;
+    if (a.sc2_dense == nullptr) {
+        const uint32_t* tight = a.tight + (size_t)b * n * W;
+        const int seed = a.seeds[(size_t)b * a.S + s];
+        for (int w = tid; w < W; w += 256) {
+            trow[w] = tight[(size_t)seed * W + w];
+            hrow[w] = a.hard[((size_t)b * n + seed) * W + w];
+        }
+        __syncthreads();
+        // 1. compact the columns where hard[seed] is set
+        for (int w = tid; w < W; w += 256) {
+            uint32_t m = hrow[w];
+            const int c = __popc(m);
+            if (c) {
+                int pos = atomicAdd(&ncand, c);
+                while (m) {
+                    const int bit = __ffs(m) - 1;
+                    m &= m - 1;
+                    keys[pos++] = 65535u - (uint32_t)(w * 32 + bit);
+                }
             }
         }
-    }
-    __syncthreads();
-    const int nc = ncand;
-    // 2. SC2[seed, j] = popc(tight[seed] & tight[j]) for those columns (warp per column)
-    for (int c = warp; c < nc; c += 8) {
-        const uint32_t jj = 65535u - keys[c];
-        const uint32_t* row = tight + (size_t)jj * W;
-        int cnt = 0;
-        for (int w = lane; w < W; w += 32) cnt += __popc(trow[w] & __ldg(row + w));
-        cnt = warp_sum_i(cnt);
-        if (lane == 0) {
-            if (cnt > 0) {
-                keys[c] = ((uint32_t)cnt << 16) | (65535u - jj);
-                atomicOr(&nzmap[jj >> 5], 1u << (jj & 31));
-            } else {
-                keys[c] = 0u;
-            }
-        }
-    }
-    __syncthreads();
-    // 3. stable top-k1 by counting: keys are distinct ((count << 16) | (65535 - j)), so the rank of a key is the
-    //    number of larger keys - no barriers inside; zero keys (SC2 == 0) are left to the tie rule below
-    if (tid == 0) ncand = 0;          // reused: number of non-zero keys
-    __syncthreads();
-    {
+        __syncthreads();
+        nc = ncand;
+        // 2. SC2[seed, j] = popc(tight[seed] & tight[j]) for those columns (warp per column)
         int nz = 0;
+        for (int c = warp; c < nc; c += 8) {
+            const uint32_t jj = 65535u - keys[c];
+            const uint32_t* row = tight + (size_t)jj * W;
+            int cnt = 0;
+            for (int w = lane; w < W; w += 32) cnt += __popc(trow[w] & __ldg(row + w));
+            cnt = warp_sum_i(cnt);
+            if (lane == 0) {
+                if (cnt > 0) {
+                    keys[c] = ((uint32_t)cnt << 16) | (65535u - jj);
+                    atomicOr(&nzmap[jj >> 5], 1u << (jj & 31));
+                    ++nz;
+                } else {
+                    keys[c] = 0u;
+                }
+            }
+        }
+        if (lane == 0 && nz) atomicAdd(&nnz, nz);
+    } else {
+        // dense rows handed in by the caller: every column is a candidate; the values are the integer counts of SC2_PCR.py:363
+        const float* row = a.sc2_dense + ((size_t)b * a.S + s) * n;
+        nc = n;
+        int nz = 0, bad = 0;
+        for (int j = tid; j < n; j += 256) {
+            const float v = __ldg(row + j);
+            const int cnt = (int)v;
+            if (!(v >= 0.f && v <= 65535.f) || (float)cnt != v) bad = 1;
+            if (cnt > 0 && !bad) {
+                keys[j] = ((uint32_t)cnt << 16) | (65535u - (uint32_t)j);
+                atomicOr(&nzmap[j >> 5], 1u << (j & 31));
+                ++nz;
+            } else {
+                keys[j] = 0u;
+            }
+        }
+        if (nz) atomicAdd(&nnz, nz);
+        if (bad) atomicOr(a.status, 1);
+    }
+    __syncthreads();
+    // 3. stable top-k1.  Keys are distinct ((count << 16) | (65535 - j)): an MSB-first radix select finds the k1-th
+    //    largest key in four 8-bit passes over the candidates, the <= k1 keys at or above it are rank-sorted.
+    //    Zero keys (SC2 == 0) are left to the tie rule below.
+    const int want = min(nnz, k1);
+    if (want > 0) {
+        uint32_t prefix = 0, pmask = 0;
+        unsigned int remaining = (unsigned int)want;
+        if (nnz > k1) {
+#pragma unroll 1
+            for (int shift = 24; shift >= 0; shift -= 8) {
+                hist[tid] = 0;
+                __syncthreads();
+                for (int c = tid; c < nc; c += 256) {
+                    const uint32_t key = keys[c];
+                    if (key != 0u && (key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+                }
+                __syncthreads();
+                // bin t is the one where the count of keys in higher bins first reaches `remaining`
+                const unsigned int h = hist[tid];
+                unsigned int incl = h;                      // inclusive suffix sum inside the warp (towards higher bins)
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int y = __shfl_down_sync(0xffffffffu, incl, o);
+                    if (lane + o < 32) incl += y;
+                }
+                if (lane == 0) wtot[warp] = incl;
+                __syncthreads();
+                unsigned int above = incl - h;
+                for (int w2 = warp + 1; w2 < 8; ++w2) above += wtot[w2];
+                if (above < remaining && remaining <= above + h) { sel_bin = (unsigned int)tid; sel_rem = remaining - above; }
+                __syncthreads();
+                prefix |= sel_bin << shift;
+                pmask |= 255u << shift;
+                remaining = sel_rem;
+            }
+        } else {
+            prefix = 1u;                                    // every non-zero key wins
+        }
         for (int c = tid; c < nc; c += 256) {
             const uint32_t key = keys[c];
-            if (key == 0u) continue;
-            ++nz;
-            int rank = 0;
-            int c2 = 0;
-            for (; c2 + 4 <= nc; c2 += 4) {
-                rank += (keys[c2] > key) + (keys[c2 + 1] > key) + (keys[c2 + 2] > key) + (keys[c2 + 3] > key);
-            }
-            for (; c2 < nc; ++c2) rank += keys[c2] > key;
-            if (rank < k1) idx1[rank] = 65535 - (int)(key & 0xffffu);
+            if (key != 0u && key >= prefix) win[atomicAdd(&nwin, 1)] = key;
         }
-        if (nz) atomicAdd(&ncand, nz);
+        __syncthreads();
+        if (tid < nwin) {
+            const uint32_t key = win[tid];
+            int rank = 0;
+            for (int c2 = 0; c2 < nwin; ++c2) rank += win[c2] > key;
+            idx1[rank] = 65535 - (int)(key & 0xffffu);
+        }
     }
     __syncthreads();
-    const int filled = min(ncand, k1);
+    const int filled = want;
     if (filled < k1 && tid == 0) {
         // remaining entries of the row are exactly 0: ties resolve to the lowest indices
         int r = filled;
@@ -914,6 +1018,32 @@ void effective_k(const eyoc_sc2_cfg* cfg, int n, int* k1, int* k2) {
     *k2 = cfg->k2;
     if (*k1 > n) { *k1 = 4; *k2 = 4; }     // SC2_PCR.py:76-78
 }
+__global__ void seed_take64_kernel(const int32_t* __restrict__ sorted_idx, int n, int S, int batch, int64_t* __restrict__ seeds) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch * S) return;
+    seeds[i] = sorted_idx[(size_t)(i / S) * n + (i % S)];
+}
+
+// SC2_PCR.py:53-57: argsort(scores, descending) -> first S per pair (stable: ties keep ascending index order)
+int rank_seeds(char* ws, const eyoc_sc2_layout& L, const float* scores, int batch, int n, int S, int32_t* seeds32, int64_t* seeds64,
+               cudaStream_t stream) {
+    const int64_t total = (int64_t)batch * n;
+    uint32_t* skeys = (uint32_t*)(ws + L.sort_keys);
+    int32_t* sidx = (int32_t*)(ws + L.sort_idx);
+    int* soffs = (int*)(ws + L.sort_offsets);
+    seed_key_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(scores, total, n, skeys, sidx);
+    EYOC_LAUNCH_CHECK();
+    segment_offsets_kernel<<<(batch + 256) / 256, 256, 0, stream>>>(soffs, batch, n);
+    EYOC_LAUNCH_CHECK();
+    size_t temp = L.sort_temp_bytes;
+    EYOC_CUDA(cub::DeviceSegmentedRadixSort::SortPairsDescending(ws + L.sort_temp, temp, skeys, skeys + total, sidx, sidx + total,
+                                                                 (int)total, batch, soffs, soffs + 1, 0, 32, stream));
+    g_eyoc_launches += 4;
+    if (seeds32) seed_take_kernel<<<(unsigned)((batch * S + 255) / 256), 256, 0, stream>>>(sidx + total, n, S, batch, seeds32);
+    else seed_take64_kernel<<<(unsigned)((batch * S + 255) / 256), 256, 0, stream>>>(sidx + total, n, S, batch, seeds64);
+    EYOC_LAUNCH_CHECK();
+    return EYOC_OK;
+}
 }  // namespace
 
 extern "C" int eyoc_sc2pcr_layout(int batch, int n, int num_seeds, const eyoc_sc2_cfg* cfg, eyoc_sc2_layout* L) {
@@ -927,6 +1057,7 @@ extern "C" int eyoc_sc2pcr_layout(int batch, int n, int num_seeds, const eyoc_sc
     L->points = c.off; c.take<Pt>(B * N);
     L->hard_bits = c.off; c.take<uint32_t>(B * N * W);
     L->tight_bits = c.off; c.take<uint32_t>(B * N * W);
+    L->near_bits = c.off; c.take<uint32_t>(B * N * W);
     L->vbuf = c.off; c.take<float>(2 * B * N);
     L->u = c.off; c.take<float>(B * N);
     L->confidence = c.off; c.take<float>(B * N);
@@ -960,6 +1091,7 @@ extern "C" int eyoc_sc2pcr_layout(int batch, int n, int num_seeds, const eyoc_sc
     L->local_notclose = c.off; c.take<int>(B * (I + 1) + B);          // notclose | local_iters
     L->best_seed = c.off; c.take<int>(B);
     L->refine_counts = c.off; c.take<int>(B * (cfg->refine_iterations + 1) + B * 16);   // counts | initial_trans (float)
+    L->status = c.off; c.take<int>(4);
     L->total = c.off;
     L->words_per_row = (int)W;
     L->k1 = k1;
@@ -1001,6 +1133,8 @@ extern "C" int eyoc_sc2pcr(const float* src, const float* tgt, int batch, int n,
     Pt* P = (Pt*)(ws + L.points);
     uint32_t* hard = (uint32_t*)(ws + L.hard_bits);
     uint32_t* tight = (uint32_t*)(ws + L.tight_bits);
+    uint32_t* near = (uint32_t*)(ws + L.near_bits);
+    int* status = (int*)(ws + L.status);
     float* vbuf = (float*)(ws + L.vbuf);
     float* u = (float*)(ws + L.u);
     float* conf = (float*)(ws + L.confidence);
@@ -1027,9 +1161,14 @@ extern "C" int eyoc_sc2pcr(const float* src, const float* tgt, int batch, int n,
     pack_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, tgt, total, P);
     EYOC_LAUNCH_CHECK();
     const bool skip_seed_stage = hooks && hooks->initial_trans;
+    const float* sc2_dense = hooks ? hooks->sc2_dense : nullptr;
+    EYOC_CHECK_ARG(!sc2_dense || (hooks->seeds && !hooks->initial_trans), "eyoc_sc2pcr: the sc2_dense hook needs the seeds hook");
     if (!skip_seed_stage) {
-        first_order_bits_kernel<<<dim3((n + 31) / 32, batch), 256, 0, stream>>>(P, n, W, cfg->d_thre, cfg->d_thre_half, hard, tight);
-        EYOC_LAUNCH_CHECK();
+        if (!sc2_dense) {       // dense SC2 rows + seeds from the caller: the bit matrices are not needed
+            first_order_bits_kernel<<<dim3((n + 31) / 32, batch), 256, 0, stream>>>(P, n, W, cfg->d_thre, cfg->d_thre_half,
+                                                                                  sqrt_threshold(cfg->nms_radius), hard, tight, near);
+            EYOC_LAUNCH_CHECK();
+        }
         const float* conf_use = conf;
         if (hooks && hooks->confidence) {
             conf_use = hooks->confidence;
@@ -1050,23 +1189,13 @@ extern "C" int eyoc_sc2pcr(const float* src, const float* tgt, int batch, int n,
         if (hooks && hooks->seeds) {
             seeds_use = hooks->seeds;
         } else {
-            nms_kernel<<<dim3((n + 31) / 32, batch), 256, 0, stream>>>(P, conf_use, n, sqrt_threshold(cfg->nms_radius), scores);
+            nms_bits_kernel<<<dim3((n + 7) / 8, batch), 256, 0, stream>>>(near, conf_use, n, W, scores);
             EYOC_LAUNCH_CHECK();
-            uint32_t* skeys = (uint32_t*)(ws + L.sort_keys);
-            int32_t* sidx = (int32_t*)(ws + L.sort_idx);
-            int* soffs = (int*)(ws + L.sort_offsets);
-            seed_key_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(scores, total, n, skeys, sidx);
-            EYOC_LAUNCH_CHECK();
-            segment_offsets_kernel<<<(batch + 256) / 256, 256, 0, stream>>>(soffs, batch, n);
-            EYOC_LAUNCH_CHECK();
-            size_t temp = L.sort_temp_bytes;
-            EYOC_CUDA(cub::DeviceSegmentedRadixSort::SortPairsDescending(ws + L.sort_temp, temp, skeys, skeys + total, sidx, sidx + total,
-                                                                         (int)total, batch, soffs, soffs + 1, 0, 32, stream));
-            g_eyoc_launches += 4;
-            seed_take_kernel<<<(unsigned)((batch * S + 255) / 256), 256, 0, stream>>>(sidx + total, n, S, batch, seeds);
-            EYOC_LAUNCH_CHECK();
+            rc = rank_seeds(ws, L, scores, batch, n, S, seeds, nullptr, stream);
+            if (rc != EYOC_OK) return rc;
         }
-        SeedArgs sa{P, hard, tight, seeds_use, n, W, S, L.k1, L.k2, I, cfg->d_thre, cfg->d_thre_sq, topk1, topk2, local_v, local_notclose};
+        SeedArgs sa{P, hard, tight, seeds_use, sc2_dense, status, n, W, S, L.k1, L.k2, I, cfg->d_thre, cfg->d_thre_sq, topk1, topk2,
+                    local_v, local_notclose};
         const size_t smem = (size_t)(3 * W + n) * sizeof(uint32_t);
         EYOC_CUDA(cudaFuncSetAttribute(seed_consensus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         seed_consensus_kernel<<<dim3(S, batch), 256, smem, stream>>>(sa);
@@ -1096,5 +1225,146 @@ extern "C" int eyoc_kabsch_batched(const float* A, const float* B, float* w, int
     if (batch == 0) return EYOC_OK;
     kabsch_kernel<<<batch, 128, 0, stream>>>(A, B, w, n, weight_threshold, T);
     EYOC_LAUNCH_CHECK();
+    return EYOC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Stage entry points on DENSE caller tensors: the public stage methods of the reference's Matcher take (and return)
+// dense [bs, n, n] / [bs, S, n] tensors (SC2_PCR.py:33-59, :170-196); the fused estimator above never forms them.
+namespace {
+struct PickLayout { size_t scores, keys, idx, offs, temp, temp_bytes, total; };
+PickLayout pick_layout(int batch, int n) {
+    PickLayout L;
+    const size_t B = batch, N = n;
+    WsCarver c(nullptr, 0);
+    L.scores = c.off; c.take<float>(B * N);
+    size_t temp = 0;
+    cub::DeviceSegmentedRadixSort::SortPairsDescending(nullptr, temp, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                                       (const int32_t*)nullptr, (int32_t*)nullptr, (int)(B * N), (int)B,
+                                                       (const int*)nullptr, (const int*)nullptr);
+    L.keys = c.off; c.take<uint32_t>(2 * B * N);
+    L.idx = c.off; c.take<int32_t>(2 * B * N);
+    L.offs = c.off; c.take<int>(B + 1);
+    L.temp = c.off; c.take<char>(temp);
+    L.temp_bytes = temp;
+    L.total = c.off;
+    return L;
+}
+
+// u = M v (warp per row, coalesced), grid (ceil(n / 8), batch)
+__global__ void __launch_bounds__(256)
+dense_matvec_kernel(const float* __restrict__ M, const float* __restrict__ vbuf, int n, int t, const int* __restrict__ done,
+                    float* __restrict__ u) {
+    if (*done) return;
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const float* row = M + ((size_t)b * n + i) * n;
+    const float* v = vbuf + ((size_t)((t + 1) & 1) * gridDim.y + b) * n;
+    float acc = 0.f;
+    if (t == 1) for (int j = lane; j < n; j += 32) acc += __ldg(row + j);                 // v0 = ones
+    else for (int j = lane; j < n; j += 32) acc = __fmaf_rn(__ldg(row + j), v[j], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) u[(size_t)b * n + i] = acc;
+}
+// v = u / (||u|| + 1e-6); not-close count of torch.allclose(v, v_prev) (SC2_PCR.py:184-186), grid (batch)
+__global__ void __launch_bounds__(256)
+dense_norm_kernel(const float* __restrict__ u, float* __restrict__ vbuf, int n, int t, const int* __restrict__ done,
+                  int* __restrict__ notclose, float* __restrict__ out) {
+    if (*done) return;
+    __shared__ double red[8];
+    __shared__ int red_i[8];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u += (size_t)b * n;
+    const float* vprev = vbuf + ((size_t)((t + 1) & 1) * gridDim.x + b) * n;
+    float* vnext = vbuf + ((size_t)(t & 1) * gridDim.x + b) * n;
+    double ss = 0.0;
+    for (int k = threadIdx.x; k < n; k += 256) ss += (double)u[k] * (double)u[k];
+    ss = warp_sum_d(ss);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    double tot = 0.0;
+    for (int k = 0; k < 8; ++k) tot += red[k];
+    const float denom = __fadd_rn((float)sqrt(tot), 1e-6f);
+    int nc = 0;
+    for (int k = threadIdx.x; k < n; k += 256) {
+        const float v = __fdiv_rn(u[k], denom);
+        const float vp = (t == 1) ? 1.0f : vprev[k];
+        const float allowed = __fadd_rn(1e-8f, fabsf(__fmul_rn(1e-5f, vp)));
+        if (!(fabsf(__fsub_rn(v, vp)) <= allowed)) nc = 1;
+        vnext[k] = v;
+        out[(size_t)b * n + k] = v;
+    }
+    nc = warp_sum_i(nc);
+    if (lane == 0) red_i[warp] = nc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int c = 0;
+        for (int k = 0; k < 8; ++k) c += red_i[k];
+        if (c) atomicAdd(notclose + t, 1);
+    }
+}
+// the stopping rule is global over the whole batch (one torch.allclose over [bs, n, 1])
+__global__ void dense_stop_kernel(const int* __restrict__ notclose, int t, int* __restrict__ done, int* __restrict__ iters) {
+    if (*done) return;
+    *iters = t;
+    if (notclose[t] == 0) *done = 1;
+}
+}  // namespace
+
+extern "C" size_t eyoc_pick_seeds_workspace_bytes(int batch, int n) {
+    if (batch < 1 || n < 1) return 0;
+    return pick_layout(batch, n).total;
+}
+
+extern "C" int eyoc_pick_seeds_dense(const float* dists, const float* scores, int batch, int n, float R, int max_num,
+                                     int64_t* seeds, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    EYOC_CHECK_ARG(dists && scores && seeds, "eyoc_pick_seeds_dense: null argument");
+    EYOC_CHECK_ARG(batch >= 1 && n >= 1 && max_num >= 0 && max_num <= n && n <= 65535, "eyoc_pick_seeds_dense: bad sizes batch=%d n=%d max_num=%d", batch, n, max_num);
+    const PickLayout P = pick_layout(batch, n);
+    if (workspace == nullptr || workspace_bytes < P.total) {
+        eyoc_set_error("eyoc_pick_seeds_dense: workspace too small (%zu < %zu)", workspace_bytes, P.total);
+        return EYOC_ERR_WORKSPACE;
+    }
+    if (max_num == 0) return EYOC_OK;
+    char* ws = (char*)workspace;
+    float* sc = (float*)(ws + P.scores);
+    nms_dense_kernel<<<dim3((n + 7) / 8, batch), 256, 0, stream>>>(dists, scores, n, R, sc);
+    EYOC_LAUNCH_CHECK();
+    eyoc_sc2_layout L;
+    memset(&L, 0, sizeof(L));
+    L.sort_keys = P.keys; L.sort_idx = P.idx; L.sort_offsets = P.offs; L.sort_temp = P.temp; L.sort_temp_bytes = P.temp_bytes;
+    return rank_seeds(ws, L, sc, batch, n, max_num, nullptr, seeds, stream);
+}
+
+extern "C" size_t eyoc_power_iteration_workspace_bytes(int batch, int n, int num_iterations) {
+    if (batch < 1 || n < 1 || num_iterations < 1) return 0;
+    return eyoc_align((size_t)3 * batch * n * sizeof(float)) + eyoc_align((size_t)(num_iterations + 4) * sizeof(int));
+}
+
+extern "C" int eyoc_power_iteration_dense(const float* M, int batch, int n, int num_iterations, float* v_out, int* iters_out,
+                                          void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    EYOC_CHECK_ARG(M && v_out, "eyoc_power_iteration_dense: null argument");
+    EYOC_CHECK_ARG(batch >= 1 && n >= 1 && num_iterations >= 1 && num_iterations <= 1024, "eyoc_power_iteration_dense: bad sizes");
+    const size_t need = eyoc_power_iteration_workspace_bytes(batch, n, num_iterations);
+    if (workspace == nullptr || workspace_bytes < need) {
+        eyoc_set_error("eyoc_power_iteration_dense: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return EYOC_ERR_WORKSPACE;
+    }
+    char* ws = (char*)workspace;
+    float* vbuf = (float*)ws;                                     // [2, batch, n]
+    float* u = vbuf + (size_t)2 * batch * n;
+    int* ctl = (int*)(ws + eyoc_align((size_t)3 * batch * n * sizeof(float)));     // done | iters | pad | notclose[1..I]
+    EYOC_CUDA(cudaMemsetAsync(ctl, 0, (size_t)(num_iterations + 4) * sizeof(int), stream));
+    int* done = ctl, *iters = ctl + 1, *notclose = ctl + 2;
+    for (int t = 1; t <= num_iterations; ++t) {
+        dense_matvec_kernel<<<dim3((n + 7) / 8, batch), 256, 0, stream>>>(M, vbuf, n, t, done, u);
+        EYOC_LAUNCH_CHECK();
+        dense_norm_kernel<<<batch, 256, 0, stream>>>(u, vbuf, n, t, done, notclose, v_out);
+        EYOC_LAUNCH_CHECK();
+        dense_stop_kernel<<<1, 1, 0, stream>>>(notclose, t, done, iters);
+        EYOC_LAUNCH_CHECK();
+    }
+    if (iters_out) EYOC_CUDA(cudaMemcpyAsync(iters_out, iters, sizeof(int), cudaMemcpyDeviceToDevice, stream));
     return EYOC_OK;
 }

@@ -98,6 +98,7 @@ struct HArgs {
     uint8_t* out; int out_packed;
     float acc_scale;                  // 2^-a: undoes the power-of-two weight pre-scale
     int K, n_out, cout, relu, l2norm, nbr_tiled;
+    int* range_status;                // bit 0 is set when a value leaves the split-half range (|x| >= 65504 or not finite), or null
     unsigned int* counters;           // [2] tile-pair hand-out counters of THIS launch (one per 128-channel part), zeroed
                                       // on the launch stream by the host wrapper: launches never share a counter
 };
@@ -477,6 +478,12 @@ sparse_conv_h_kernel(HArgs a) {
                     }
                     if (rowv[u] >= 0) {
                         uint8_t* orow_p = a.out + (size_t)rowv[u] * row_bytes;
+                        if (a.out_packed && a.range_status) {         // fp16 hi cannot hold it: the fp32 reference can
+                            bool bad = false;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) bad |= !(fabsf(y[j]) < 65504.f);
+                            if (bad) atomicOr(a.range_status, 1);
+                        }
                         if (a.out_packed) xh_store8(orow_p, col, y);
                         else {
                             *reinterpret_cast<float4*>(orow_p + (size_t)col * 4) = make_float4(y[0], y[1], y[2], y[3]);
@@ -652,7 +659,7 @@ __global__ void split_weights_h_kernel(const float* __restrict__ w, int K, int c
 }
 
 // fp32 [n, c] <-> split-half rows; one thread per 8 channels
-__global__ void xh_pack_kernel(const float* __restrict__ x, long long n8, int c, uint8_t* __restrict__ xh) {
+__global__ void xh_pack_kernel(const float* __restrict__ x, long long n8, int c, uint8_t* __restrict__ xh, int* __restrict__ range_status) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n8) return;
     const int c8n = c >> 3;
@@ -661,6 +668,12 @@ __global__ void xh_pack_kernel(const float* __restrict__ x, long long n8, int c,
     const float4 a0 = __ldg(reinterpret_cast<const float4*>(x + r * c + col));
     const float4 a1 = __ldg(reinterpret_cast<const float4*>(x + r * c + col + 4));
     const float y[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    if (range_status) {
+        bool bad = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bad |= !(fabsf(y[j]) < 65504.f);
+        if (bad) atomicOr(range_status, 1);
+    }
     xh_store8(xh + (size_t)r * c * 4, col, y);
 }
 __global__ void xh_unpack_kernel(const uint8_t* __restrict__ xh, long long n8, int c, float* __restrict__ x) {
@@ -768,11 +781,11 @@ extern "C" int eyoc_convh_split_weights(const float* weight, int K, int cin, int
     return EYOC_OK;
 }
 
-extern "C" int eyoc_xh_pack(const float* x, int64_t n, int c, void* xh, cudaStream_t stream) {
+extern "C" int eyoc_xh_pack(const float* x, int64_t n, int c, void* xh, int32_t* range_status, cudaStream_t stream) {
     EYOC_CHECK_ARG(x && xh && n >= 0 && c >= 32 && c % 32 == 0, "eyoc_xh_pack: bad argument (c must be a multiple of 32)");
     if (n == 0) return EYOC_OK;
     const long long n8 = (long long)n * (c / 8);
-    xh_pack_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>(x, n8, c, (uint8_t*)xh);
+    xh_pack_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>(x, n8, c, (uint8_t*)xh, range_status);
     EYOC_LAUNCH_CHECK();
     return EYOC_OK;
 }
@@ -806,7 +819,7 @@ extern "C" int eyoc_sparse_conv_h(const void* in0, int c0, const void* in1, int 
                                   const int32_t* row_perm, int nbr_tiled, const uint32_t* tile_masks, const void* wt_img,
                                   float acc_scale, const float* scale, const float* shift, const void* residual,
                                   int residual_packed, int relu, int l2norm, void* out, int out_packed, int cout,
-                                  uint32_t* counters, cudaStream_t stream) {
+                                  int32_t* range_status, uint32_t* counters, cudaStream_t stream) {
     EYOC_CHECK_ARG(in0 && wt_img && out && counters, "eyoc_sparse_conv_h: null argument");
     EYOC_CHECK_ARG((in1 != nullptr) == (c1 > 0), "eyoc_sparse_conv_h: in1 and c1 must be given together");
     EYOC_CHECK_ARG(nbr || K == 1, "eyoc_sparse_conv_h: a neighbour table is required when K > 1");
@@ -819,7 +832,7 @@ extern "C" int eyoc_sparse_conv_h(const void* in0, int c0, const void* in1, int 
     if (n_out == 0) return EYOC_OK;
     HArgs a{(const uint8_t*)in0, c0, (const uint8_t*)in1, c1, nbr, row_perm, tile_masks, (const __half*)wt_img, scale, shift,
             (const uint8_t*)residual, residual_packed, (uint8_t*)out, out_packed, acc_scale, K, (int)n_out, cout, relu, l2norm,
-            nbr_tiled, counters};
+            nbr_tiled, range_status, counters};
     if (cout <= 64) return launch_h<false, 2, 6>(a, stream);       // 6 x 32 KB X stages + 2 x 16 KB weight slabs
     return launch_h<true, 2, 5>(a, stream);                          // 5 x 32 KB X stages + 2 x 32 KB weight slabs
 }

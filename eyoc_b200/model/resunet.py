@@ -8,6 +8,7 @@ place, final L2 normalisation in the last epilogue) instead of ~90 separate Mink
 import torch
 import torch.nn as nn
 
+from .. import nn as enn
 from ..nn import MinkowskiConvolution, MinkowskiConvolutionTranspose, conv_bn_act
 from ..sparse import SparseTensor
 from .common import get_norm
@@ -64,11 +65,33 @@ class ResUNet2(nn.Module):
         self.conv1_tr = conv(CHANNELS[1] + TR_CHANNELS[2], TR_CHANNELS[1], 1)
         self.final = conv(TR_CHANNELS[1], out_channels, 1, bias=True)
 
+    # The default data path keeps activations as fp16 hi/lo pairs (|x| < 65504).  The kernels raise a device flag when a value
+    # leaves that range (the fp32 reference would carry on); forward() reads it once per call (one 4-byte D2H) and, if set,
+    # runs the network again through the fp32-activation tensor-core path ('tf32x3').  Set False to skip the read.
+    RANGE_CHECK = True
+
     def forward(self, x):
-        """model/resunet.py:142-193.  The MEF.relu calls after each block (:146,151,156,161,166,173,180) are
-        idempotent (the block already ends in ReLU, residual_block.py:51) and therefore cost nothing here."""
+        """model/resunet.py:142-193 (see _forward) + the split-half range guard."""
         if self.training:
             raise NotImplementedError('eyoc_b200 implements the inference path only: call model.eval()')
+        out = self._forward(x)
+        if self.RANGE_CHECK and enn.CONV_MODE == 'f16x3':
+            mgr = x.coordinate_manager
+            if int(mgr.range_status.item()) & 1:
+                import warnings
+                warnings.warn('activations beyond the fp16 hi/lo range (|x| >= 65504 or non-finite): re-running this forward '
+                              "pass with fp32 activations (CONV_MODE 'tf32x3')")
+                mgr.range_status.zero_()
+                enn.CONV_MODE = 'tf32x3'
+                try:
+                    out = self._forward(x)
+                finally:
+                    enn.CONV_MODE = 'f16x3'
+        return out
+
+    def _forward(self, x):
+        """model/resunet.py:142-193.  The MEF.relu calls after each block (:146,151,156,161,166,173,180) are
+        idempotent (the block already ends in ReLU, residual_block.py:51) and therefore cost nothing here."""
         with torch.no_grad():
             out_s1 = self.block1(conv_bn_act(x, self.conv1, self.norm1))
             out_s2 = self.block2(conv_bn_act(out_s1, self.conv2, self.norm2))

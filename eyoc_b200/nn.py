@@ -153,7 +153,7 @@ def h_supported(c0, c1, cout, K, l2norm):
 
 
 def sparse_conv_h_raw(in0, in1, nbr, weight, scale, shift, residual, relu, l2norm, out, row_perm=None, nbr_tiled=False,
-                      tile_masks=None, h_img=None):
+                      tile_masks=None, h_img=None, range_status=None):
     """Thin call into eyoc_sparse_conv_h.  in0 / in1 split-half [n, 2 c] fp16; residual and out are split-half when
     their dtype is fp16, fp32 rows otherwise; h_img = cached ``split_weights_h(weight)``."""
     _C.require_cuda(in0, in1, nbr, weight, scale, shift, residual, out, row_perm, tile_masks)
@@ -177,7 +177,7 @@ def sparse_conv_h_raw(in0, in1, nbr, weight, scale, shift, residual, relu, l2nor
             _C.ptr(row_perm), _C.c_int(int(nbr_tiled)), _C.ptr(tile_masks), _C.ptr(img), _C.c_float(acc_scale), _C.ptr(scale),
             _C.ptr(shift), _C.ptr(residual), _C.c_int(int(residual is not None and residual.dtype == torch.float16)),
             _C.c_int(int(relu)), _C.c_int(int(l2norm)), _C.ptr(out), _C.c_int(int(out.dtype == torch.float16)), _C.c_int(cout),
-            _C.ptr(counters), _C.stream()))
+            _C.ptr(range_status), _C.ptr(counters), _C.stream()))
     if ev is not None:
         ev[1].record()
         PROFILE.append((ev[0], ev[1], dict(K=K, cin=c0 + c1, cout=cout, n_out=out.shape[0], nbr=nbr,
@@ -282,7 +282,7 @@ def conv_bn_act(x, conv, norm=None, residual=None, relu=False, l2norm=False, ski
                           dtype=torch.float32 if l2norm else torch.float16, device=dev)
         sparse_conv_h_raw(x.Fh, skip.Fh if skip is not None else None, nbr, conv.kernel.detach(), scale, shift,
                           residual.Fh if residual is not None else None, relu, l2norm, out, row_perm, tiled, masks,
-                          h_img=conv.h_image())
+                          h_img=conv.h_image(), range_status=mgr.range_status)
         if l2norm:
             return SparseTensor(out, coordinate_map_key=key, coordinate_manager=mgr)
         return SparseTensor(features_xh=out, coordinate_map_key=key, coordinate_manager=mgr)

@@ -143,16 +143,21 @@ class _Cfg(dict):
 
 
 def build_model(config, device):
-    """scripts/test_kitti.py:81-93; a missing checkpoint falls back to seeded random weights (there is none to download)."""
+    """scripts/test_kitti.py:81-93.  With ``--save_dir`` the checkpoint must exist (the reference raises inside torch.load;
+    a mistyped directory must not turn into an evaluation of random weights).  Without a save_dir - the synthetic mode,
+    where no checkpoint is reachable - the weights are seeded random-init, and the log says so."""
     from ..model import load_model
     Model = load_model(config.model)
     model = Model(1, config.model_n_out, bn_momentum=config.bn_momentum, conv1_kernel_size=config.conv1_kernel_size,
                   normalize_feature=config.normalize_feature)
     ckpt = os.path.join(config.save_dir, 'best_val_checkpoint.pth') if config.get('save_dir') else None
-    if ckpt and os.path.exists(ckpt):
+    if ckpt is not None:
+        if not os.path.exists(ckpt):
+            raise FileNotFoundError(f'{ckpt}: no checkpoint under --save_dir (omit --save_dir to evaluate seeded random-init '
+                                    'weights on synthetic pairs)')
         model.load_state_dict(torch.load(ckpt, map_location='cpu')['state_dict'])
     else:
-        logging.info('no checkpoint: seeded random-init weights')
+        logging.warning('no --save_dir: seeded RANDOM-INIT weights (recall figures carry no meaning)')
         torch.manual_seed(0)
         model.apply(lambda m: m.reset_parameters() if hasattr(m, 'reset_parameters') and not isinstance(m, torch.nn.BatchNorm1d) else None)
     return model.to(device).eval()

@@ -63,7 +63,9 @@ class CoordinateManager:
         self._tile_masks = {}
         self._perms = {}
         self.max_batch = 0
-        self._status = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self._status = torch.zeros(3, dtype=torch.int32, device=self.device)
+        # [2]: bit 0 set by the split-half kernels when a value does not fit the fp16 hi/lo format (nn.CONV_MODE 'f16x3')
+        self.range_status = self._status[2:3]
         c = coordinates.to(torch.int32).contiguous()
         lv = _Level()
         lv.coords, lv.n, lv.ts = c, c.shape[0], 1
@@ -79,7 +81,7 @@ class CoordinateManager:
     # ------------------------------------------------------------------ levels
     def _check_status(self):
         if not self._checked:
-            st, self.max_batch = (int(v) for v in self._status.tolist())
+            st, self.max_batch = (int(v) for v in self._status[:2].tolist())
             if st & 1:
                 raise RuntimeError('coordinates outside the packed 16-bit range (batch 0..65535, xyz -32768..32767)')
             if st & 2:
@@ -196,14 +198,14 @@ class CoordinateManager:
         return self._perms[ts]
 
 
-def xh_pack(x):
+def xh_pack(x, range_status=None):
     """fp32 [n, c] (c % 32 == 0) -> split-half rows [n, 2 c] fp16 (eyoc_xh_pack)."""
     _C.require_cuda(x)
     x = x.to(torch.float32).contiguous()
     n, c = x.shape
     out = torch.empty((n, 2 * c), dtype=torch.float16, device=x.device)
     with torch.cuda.device(x.device):
-        _C.check(_C.lib().eyoc_xh_pack(_C.ptr(x), _C.c_int64(n), _C.c_int(c), _C.ptr(out), _C.stream()))
+        _C.check(_C.lib().eyoc_xh_pack(_C.ptr(x), _C.c_int64(n), _C.c_int(c), _C.ptr(out), _C.ptr(range_status), _C.stream()))
     return out
 
 
@@ -259,7 +261,7 @@ class SparseTensor:
     def Fh(self):
         """Split-half image of the features (packed on first access; needs C % 32 == 0)."""
         if self._Fh is None:
-            self._Fh = xh_pack(self._F)
+            self._Fh = xh_pack(self._F, self.coordinate_manager.range_status)
         return self._Fh
 
     @property

@@ -75,13 +75,16 @@ typedef struct {
     const float* confidence;      /* [batch, n]      skip the leading-eigenvector stage        */
     const int32_t* seeds;         /* [batch, S]      skip NMS + ranking                        */
     const float* initial_trans;   /* [batch, 4, 4]   skip the whole seed stage                 */
+    const float* sc2_dense;       /* [batch, S, n]   caller's second-order measure (integer-valued, SC2_PCR.py:363) instead
+                                     of the bit-matrix one; needs `seeds` (drop-in Matcher.cal_seed_trans)             */
 } eyoc_sc2_hooks;
 
 /* Byte offsets of the intermediate buffers inside the workspace (for tests and diagnostics). */
 typedef struct {
     size_t points, hard_bits, tight_bits, vbuf, u, confidence, scores, seeds, topk1, topk2, local_v,
         seed_weights, seed_trans, counters, global_iters, local_notclose, best_seed, refine_counts, total,
-        csr_rowptr, csr_cols, csr_vals, csr_capacity, sort_keys, sort_idx, sort_offsets, sort_temp, sort_temp_bytes;
+        csr_rowptr, csr_cols, csr_vals, csr_capacity, sort_keys, sort_idx, sort_offsets, sort_temp, sort_temp_bytes,
+        near_bits, status;
     int words_per_row, k1, k2, num_seeds;
 } eyoc_sc2_layout;
 
@@ -92,6 +95,20 @@ size_t eyoc_sc2pcr_workspace_bytes(int batch, int n, int num_seeds, const eyoc_s
 int eyoc_sc2pcr(const float* src, const float* tgt, int batch, int n, int num_seeds, const eyoc_sc2_cfg* cfg,
                 const eyoc_sc2_hooks* hooks, void* workspace, size_t workspace_bytes, float* trans, float* fitness,
                 float* labels, eyoc_stream_t stream);
+
+/* Stage entry points on DENSE caller tensors (the reference's public Matcher stage methods take dense matrices; the fused
+ * estimator above never forms them).
+ * scripts/SC2_PCR/SC2_PCR.py:33-59 pick_seeds: dists [batch, n, n], scores [batch, n] -> seeds [batch, max_num] int64
+ * (NMS: i survives iff for all j score_i >= score_j or dists_ij >= R; then descending score, ties by lowest index). */
+size_t eyoc_pick_seeds_workspace_bytes(int batch, int n);
+int eyoc_pick_seeds_dense(const float* dists, const float* scores, int batch, int n, float R, int max_num, int64_t* seeds,
+                          void* workspace, size_t workspace_bytes, eyoc_stream_t stream);
+/* scripts/SC2_PCR/SC2_PCR.py:179-190 cal_leading_eigenvector(method='power'): M [batch, n, n] -> v [batch, n];
+ * v <- M v / (||M v|| + 1e-6) from ones, at most num_iterations times, stopping when torch.allclose(v, v_prev) holds over
+ * the WHOLE batch (one allclose call in the reference).  iters_out (device int, may be NULL) = iterations run. */
+size_t eyoc_power_iteration_workspace_bytes(int batch, int n, int num_iterations);
+int eyoc_power_iteration_dense(const float* M, int batch, int n, int num_iterations, float* v_out, int* iters_out,
+                               void* workspace, size_t workspace_bytes, eyoc_stream_t stream);
 
 /* scripts/SC2_PCR/common.py:7-45 rigid_transform_3d: A, B [batch, n, 3], w [batch, n] (NULL = ones;
  * negative weights are zeroed IN PLACE like common.py:20) -> T [batch, 4, 4]. */
@@ -187,19 +204,23 @@ int eyoc_sparse_conv_tc(const float* in0, int c0, const float* in1, int c1, cons
  * Weights: wt_img = eyoc_convh_split_weights(weight * wscale) with wscale a power of two chosen by the caller so that
  * max |w| * wscale lies in [2^13, 2^14); acc_scale = 1 / wscale undoes it (exactly) in the epilogue.
  * tile_masks [ceil(n_out / 256)] (eyoc_tile_masks of the tiled table) or NULL (each CTA then derives its own).
+ * range_status (device int32, may be NULL; also on eyoc_xh_pack): bit 0 is OR-ed in when a value written in the split-half
+ * format is not representable (|x| >= 65504 or not finite) where the fp32 reference would carry on: the caller re-runs in
+ * the tf32 / fp32 data path (eyoc_b200.model.ResUNet2.forward does).
  * counters: 8 bytes of caller-owned device scratch PER LAUNCH (the persistent grid's tile-pair hand-out counters; cleared
  * here in stream order, so concurrent launches on any number of streams never share state).
  * Supported shapes as reported by eyoc_sparse_conv_h_supported (those of the tf32 path). */
 size_t eyoc_convh_weight_image_halves(int K, int cin, int cout);
 int eyoc_convh_split_weights(const float* weight, int K, int cin, int cout, float wscale, void* wt_img, eyoc_stream_t stream);
-int eyoc_xh_pack(const float* x, int64_t n, int c, void* xh, eyoc_stream_t stream);
+int eyoc_xh_pack(const float* x, int64_t n, int c, void* xh, int32_t* range_status, eyoc_stream_t stream);
 int eyoc_xh_unpack(const void* xh, int64_t n, int c, float* x, eyoc_stream_t stream);
 int eyoc_tile_masks(const int32_t* nbr_tiled, int K, int64_t n_out, uint32_t* masks, eyoc_stream_t stream);
 int eyoc_sparse_conv_h_supported(int c0, int c1, int cout, int K, int l2norm);
 int eyoc_sparse_conv_h(const void* in0, int c0, const void* in1, int c1, const int32_t* nbr, int K, int64_t n_out,
                        const int32_t* row_perm, int nbr_tiled, const uint32_t* tile_masks, const void* wt_img,
                        float acc_scale, const float* scale, const float* shift, const void* residual, int residual_packed,
-                       int relu, int l2norm, void* out, int out_packed, int cout, uint32_t* counters, eyoc_stream_t stream);
+                       int relu, int l2norm, void* out, int out_packed, int cout, int32_t* range_status, uint32_t* counters,
+                       eyoc_stream_t stream);
 /* Test aid: cap gridDim.x of the persistent grid (0 = one CTA per SM), so that small inputs walk many tile pairs per CTA. */
 int eyoc_debug_convh_grid_cap(int max_ctas);
 /* Measurement aids of the split-half kernel, as eyoc_debug_conv_ablate / eyoc_debug_conv_times above. */

@@ -45,7 +45,7 @@ def se3_transform(pts, trans):
 
 def se3_integrate(R, t):
     """scripts/SC2_PCR/utils/SE3.py:73-96 (batched torch branch)."""
-    T = torch.eye(4)[None].repeat(R.shape[0], 1, 1)
+    T = torch.eye(4)[None].repeat(R.shape[0], 1, 1).to(R.device)
     T[:, :3, :3] = R
     T[:, :3, 3:4] = t.view([-1, 3, 1])
     return T
@@ -64,9 +64,10 @@ def kabsch_weighted(A, B, weights=None, weight_threshold=0):
     Am = A - cA
     Bm = B - cB
     H = Am.permute(0, 2, 1) @ torch.diag_embed(weights) @ Bm        # :33-34
-    U, S, V = torch.svd(H)                                           # :36 (CPU LAPACK)
+    U, S, V = torch.svd(H.cpu())                                     # :36 (LAPACK on the CPU whatever the device)
+    U, S, V = U.to(weights.device), S.to(weights.device), V.to(weights.device)   # :37
     delta = torch.det(V @ U.permute(0, 2, 1))
-    eye = torch.eye(3)[None].repeat(bs, 1, 1)
+    eye = torch.eye(3)[None].repeat(bs, 1, 1).to(A.device)
     eye[:, -1, -1] = delta
     R = V @ eye @ U.permute(0, 2, 1)
     t = cB.permute(0, 2, 1) - R @ cA.permute(0, 2, 1)
@@ -82,8 +83,9 @@ def kabsch_weighted_nodiag(A, B, weights):
     cA = torch.sum(A * weights[:, :, None], dim=1, keepdim=True) / wsum
     cB = torch.sum(B * weights[:, :, None], dim=1, keepdim=True) / wsum
     H = (A - cA).permute(0, 2, 1) * weights[:, None, :] @ (B - cB)
-    U, S, V = torch.svd(H)
-    eye = torch.eye(3)[None].repeat(A.shape[0], 1, 1)
+    U, S, V = torch.svd(H.cpu())
+    U, V = U.to(A.device), V.to(A.device)
+    eye = torch.eye(3)[None].repeat(A.shape[0], 1, 1).to(A.device)
     eye[:, -1, -1] = torch.det(V @ U.permute(0, 2, 1))
     R = V @ eye @ U.permute(0, 2, 1)
     return se3_integrate(R, cB.permute(0, 2, 1) - R @ cA.permute(0, 2, 1))

@@ -186,3 +186,45 @@ def test_forward_fat_variant_vs_oracle():
     model = model.cuda().eval()
     got = model(SparseTensor(feats.cuda(), coordinates=torch.from_numpy(coords).cuda())).F.cpu()
     assert float((got - want).abs().max()) <= 1e-5, float((got - want).abs().max())
+
+
+def test_range_guard_falls_back_to_fp32_activations():
+    """A checkpoint whose activations leave the fp16 hi/lo range (|x| >= 65504): the kernels flag it on the device and
+    forward() re-runs through the fp32-activation path - finite features within tolerance of the fp32 oracle, where the
+    split-half path alone would have produced Inf / NaN.  An in-range checkpoint leaves the flag clear."""
+    import warnings
+    from eyoc_b200 import nn as enn
+    from eyoc_b200.model import load_model
+    from eyoc_b200.sparse import SparseTensor
+    from oracle import resunet_oracle as RO
+    from tests.test_resunet_gpu import _cloud
+    coords = _cloud(1500, 6, batch=2)
+    feats = torch.ones((len(coords), 1), dtype=torch.float32)
+    sd = RO.make_state_dict(1, 32, 5, seed=8)
+    sd['conv1.kernel'] = sd['conv1.kernel'] * 3.0e6
+    model = load_model('ResUNetBN2C')(1, 32, bn_momentum=0.05, normalize_feature=True, conv1_kernel_size=5, D=3)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    want = RO.resunet_forward(coords, feats, sd, True, 5)
+    assert bool(torch.isfinite(want).all())
+    x = SparseTensor(feats.cuda(), coordinates=torch.from_numpy(coords).cuda())
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        got = model(x).F.cpu()
+    assert any('fp16 hi/lo range' in str(m.message) for m in w)
+    assert enn.CONV_MODE == 'f16x3'                                   # restored
+    assert bool(torch.isfinite(got).all())
+    assert float((got - want).abs().max()) <= 2e-5, float((got - want).abs().max())
+    # without the guard the same forward is not finite (this is what the flag protects against)
+    model.RANGE_CHECK = False
+    raw = model(SparseTensor(feats.cuda(), coordinates=torch.from_numpy(coords).cuda())).F
+    assert not bool(torch.isfinite(raw).all())
+    # in-range weights: no flag, no warning
+    sd2 = RO.make_state_dict(1, 32, 5, seed=8)
+    model.load_state_dict(sd2)
+    model.RANGE_CHECK = True
+    x2 = SparseTensor(feats.cuda(), coordinates=torch.from_numpy(coords).cuda())
+    with warnings.catch_warnings(record=True) as w2:
+        warnings.simplefilter('always')
+        model(x2)
+    assert not w2 and int(x2.coordinate_manager.range_status.item()) == 0

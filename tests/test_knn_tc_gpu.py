@@ -48,6 +48,25 @@ def test_wide_norm_range_and_offsets(form):
     _check(q.cuda(), r.cuda(), form)
 
 
+@pytest.mark.parametrize('scale', [1.05, 1.5, 2.0])
+def test_form1_products_above_one_give_first_nan(scale):
+    """Un-normalised descriptors with norms just above 1 .. around 2: wherever <q, r> > 1 the compared value
+    sqrt(2 - 2 s + 1e-6) is NaN and torch.argmin / the fp32 kernel return the FIRST such column whatever its s - the
+    pre-filter must not drop an earlier NaN column for lying far below the row maximum."""
+    g = torch.Generator().manual_seed(int(scale * 100))
+    q = _unit(g, 2, 1500, 32) * scale
+    r = _unit(g, 2, 2300, 32) * scale
+    # a few strongly aligned references per query at scattered indices, so several columns exceed 1 by different margins
+    for b in range(2):
+        for k in range(0, 1500, 3):
+            j = (k * 7 + 11) % 2300
+            r[b, j] = q[b, k] * (0.7 + 0.3 * ((k % 5) / 4.0))
+    i0, d0, i1, d1 = _both(q, r, 1)
+    assert bool(torch.isnan(d0).any())                              # the case is exercised
+    assert torch.equal(i0, i1), f'{int((i0 != i1).sum())} of {i0.numel()} indices differ'
+    assert torch.equal(d0.view(torch.int32), d1.view(torch.int32))
+
+
 @pytest.mark.parametrize('form', [0, 1])
 def test_clustered_near_duplicates_and_exact_ties(form):
     """Many reference rows within 1e-4 .. 1e-7 of each other (the pre-filter must keep every possible winner), plus exact

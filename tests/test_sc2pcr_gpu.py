@@ -86,21 +86,134 @@ def test_stage_parity_with_oracle_upstream(golden_dir, name):
     assert int((labels3[0].cpu().numpy() != g['st_labels']).sum()) == 0
 
 
-def test_first_order_bits_bit_exact(golden_dir):
-    """hard / tight compatibility bit matrices vs the oracle's dense fp32 masks (SC2_PCR.py:333-342,357)."""
+def _ocfg(cfg, **kw):
     from oracle import sc2pcr_oracle as O
-    g, cfg, src, tgt = _load(golden_dir, 'sc2pcr_n1000_s1')
+    return O.SC2Config(**{k: cfg[k] for k in ('inlier_threshold', 'num_node', 'd_thre', 'num_iterations', 'ratio',
+                                               'nms_radius', 'max_points', 'k1', 'k2')}, **kw)
+
+
+@pytest.mark.parametrize('name', ['sc2pcr_n1000_s1', 'sc2pcr_n2000_s3', 'sc2pcr_n25_s4'])
+def test_first_order_bits_bit_exact(golden_dir, name):
+    """hard / tight compatibility bit matrices vs the oracle's dense fp32 masks (SC2_PCR.py:333-342,357) and the NMS
+    neighbourhood bits vs `src_dist >= R` (SC2_PCR.py:50).  The kernel classifies with approximate square roots and falls
+    back to the exact ones near a threshold: the bits must be the exact evaluation's everywhere."""
+    from oracle import sc2pcr_oracle as O
+    g, cfg, src, tgt = _load(golden_dir, name)
     m = _matcher(cfg)
     det = {}
     m._run(src, tgt, want_labels=False, detail=det)
-    ocfg = O.SC2Config(**{k: cfg[k] for k in ('inlier_threshold', 'num_node', 'd_thre', 'num_iterations', 'ratio',
-                                               'nms_radius', 'max_points', 'k1', 'k2')})
-    _, _, _, hard, tight = O.first_order(src.cpu(), tgt.cpu(), ocfg)
+    src_dist, _, _, hard, tight = O.first_order(src.cpu(), tgt.cpu(), _ocfg(cfg))
+    near = (~(src_dist >= cfg['nms_radius'])).float()
     n = src.shape[1]
-    for name, want in (('hard_bits', hard), ('tight_bits', tight)):
-        words = det[name][0].cpu().numpy().view(np.uint32)
+    for key, want in (('hard_bits', hard), ('tight_bits', tight), ('near_bits', near)):
+        words = det[key][0].cpu().numpy().view(np.uint32)
         bits = ((words[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(n, -1)[:, :n]
-        np.testing.assert_array_equal(bits.astype(np.float32), want[0].numpy())
+        np.testing.assert_array_equal(bits.astype(np.float32), want[0].numpy(), err_msg=key)
+
+
+def test_first_order_bits_near_threshold_stress():
+    """Correspondences constructed so that thousands of cross distances land within a few ulp of d_thre and d_thre / 2
+    (the zone where the approximate classification must hand over to the exact one), at small and large coordinates."""
+    from oracle import sc2pcr_oracle as O
+    from eyoc_b200.scripts.SC2_PCR.SC2_PCR import Matcher
+    rng = np.random.default_rng(11)
+    n = 1024
+    src = rng.uniform(-60, 60, (n, 3)).astype(np.float32)
+    tgt = src.copy()
+    # shift target points along x by multiples of 0.05 / 0.1 plus a few ulp: |ds - dt| clusters on the thresholds
+    steps = rng.integers(0, 4, n).astype(np.float32)
+    tgt[:, 0] = src[:, 0] * np.float32(1.0) + steps * np.float32(0.05) + rng.integers(-3, 4, n).astype(np.float32) * np.float32(2 ** -20)
+    src[:, 1:] = 0
+    tgt[:, 1:] = 0                       # collinear: ds = |dx|, dt = |dx + k 0.05 + eps|, cross = |k 0.05 + eps| exactly representable-ish
+    src[n // 2:] *= np.float32(100.0)    # large coordinates: wide error margin
+    tgt[n // 2:] = src[n // 2:] + (tgt[n // 2:] - src[n // 2:] / np.float32(100.0))
+    s, t = torch.from_numpy(src)[None], torch.from_numpy(tgt)[None]
+    cfg = dict(inlier_threshold=0.6, num_node='all', d_thre=0.1, num_iterations=20, ratio=0.2, nms_radius=0.6, max_points=8000, k1=30, k2=20)
+    m = Matcher(use_mutual=False, **cfg)
+    det = {}
+    m._run(s.cuda(), t.cuda(), want_labels=False, detail=det)
+    src_dist, cross, _, hard, tight = O.first_order(s, t, _ocfg(cfg))
+    close = ((cross - 0.1).abs() < 1e-5) | ((cross - 0.05).abs() < 1e-5)
+    assert int(close.sum()) > 2000, int(close.sum())            # the stress really sits on the thresholds
+    for key, want in (('hard_bits', hard), ('tight_bits', tight)):
+        words = det[key][0].cpu().numpy().view(np.uint32)
+        bits = ((words[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(n, -1)[:, :n]
+        np.testing.assert_array_equal(bits.astype(np.float32), want[0].numpy(), err_msg=key)
+
+
+@pytest.mark.parametrize('name', ['sc2pcr_n1000_s1', 'sc2pcr_n2000_s2'])
+def test_matcher_stage_methods(golden_dir, name):
+    """The public stage methods of the drop-in Matcher on the dense tensors the reference hands them
+    (SC2_PCR.py:33-59, :61-168, :170-196, :238-278) vs the pinned oracle stage functions."""
+    from oracle import sc2pcr_oracle as O
+    g, cfg, src, tgt = _load(golden_dir, name)
+    m = _matcher(cfg)
+    ocfg = _ocfg(cfg, stable_ties=True)
+    det = {}
+    O.sc2_pcr(src.cpu().clone(), tgt.cpu().clone(), ocfg, det)
+    src_dist, cross, SC, hard, tight = O.first_order(src.cpu(), tgt.cpu(), ocfg)
+    n = src.shape[1]
+    S = int(n * cfg['ratio'])
+    # cal_leading_eigenvector on the dense soft matrix
+    conf = m.cal_leading_eigenvector(SC.cuda(), method='power')
+    assert conf.shape == (1, n)
+    np.testing.assert_allclose(conf[0].cpu().numpy(), g['confidence'], rtol=2e-4, atol=1e-7)
+    with pytest.raises(NotImplementedError):
+        m.cal_leading_eigenvector(SC.cuda(), method='eig')
+    # ... and on a batch of small matrices (the shape cal_seed_trans uses it on), one global stopping rule
+    gen = torch.Generator().manual_seed(3)
+    Mb = torch.rand(37, 20, 20, generator=gen)
+    Mb = (Mb + Mb.transpose(1, 2)) / 2
+    want_v, _ = O.power_iteration(Mb, cfg['num_iterations'])
+    np.testing.assert_allclose(m.cal_leading_eigenvector(Mb.cuda()).cpu().numpy(), want_v.numpy(), rtol=1e-4, atol=1e-7)
+    # pick_seeds on the dense distance matrix, fed the reference's confidence: the stable-rule seed list, bit for bit
+    conf_ref = torch.from_numpy(g['confidence'])[None]
+    seeds = m.pick_seeds(src_dist.cuda(), conf_ref.cuda(), R=cfg['nms_radius'], max_num=S)
+    assert seeds.dtype == torch.int64 and seeds.shape == (1, S)
+    np.testing.assert_array_equal(seeds[0].cpu().numpy(), g['st_seeds'])
+    assert torch.equal(seeds.cpu(), O.pick_seeds(src_dist, conf_ref, cfg['nms_radius'], S, stable=True))
+    # cal_seed_trans on the oracle's dense second-order measure
+    T0, fit = m.cal_seed_trans(det['seeds'].cuda(), det['SC2'].cuda(), src, tgt)
+    _pose_close(T0[0].cpu().numpy(), g['st_initial_trans'])
+    fit_gpu, fit_ref = fit[0].cpu().numpy(), g['st_fitness']
+    assert np.abs(fit_gpu - fit_ref).max() <= 2 and (fit_gpu != fit_ref).mean() < 0.02
+    T0b, fitb, _ = m._run(src, tgt, want_labels=False, refine_iterations=0, hooks=dict(seeds=det['seeds']))
+    assert torch.equal(T0, T0b) and torch.equal(fit, fitb)        # dense-SC2 route == bit-matrix route
+    bad = det['SC2'].clone()
+    bad[0, 0, 0] = 0.5
+    with pytest.raises(RuntimeError):
+        m.cal_seed_trans(det['seeds'].cuda(), bad.cuda(), src, tgt)
+    # post_refinement from the oracle's initial transform
+    T = m.post_refinement(torch.from_numpy(g['st_initial_trans'])[None].cuda(), src, tgt, 20)
+    _pose_close(T[0].cpu().numpy(), g['st_final_trans'])
+    assert torch.equal(m.post_refinement(T0, src, tgt, 0), T0)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_stage_parity_vs_torch_cuda(golden_dir, name):
+    """The tie rule, pinned on the reference's real backend: `cuda_*` goldens are the reference's torch ops run on
+    torch-CUDA with plain argsort(descending=True) (oracle/pin_cuda_reference.py, generated on a B200).  Fed the torch-CUDA
+    upstream tensors through the hooks, the kernels' seed list and top-k index sets must be those bit for bit."""
+    import os
+    path = f'{golden_dir}/cuda_{name}.npz'
+    if not os.path.exists(path):
+        pytest.skip('cuda goldens not generated yet (python -m oracle.pin_cuda_reference on a GPU box)')
+    g, cfg, src, tgt = _load(golden_dir, name)
+    c = np.load(path)
+    m = _matcher(cfg)
+    det = {}
+    m._run(src, tgt, want_labels=True, detail=det, hooks=dict(confidence=torch.from_numpy(c['cuda_confidence'])[None]))
+    np.testing.assert_array_equal(det['seeds'][0].cpu().numpy(), c['cuda_seeds'])
+    det = {}
+    T, fit, labels = m._run(src, tgt, want_labels=True, detail=det, hooks=dict(seeds=torch.from_numpy(c['cuda_seeds'])[None]))
+    np.testing.assert_array_equal(det['topk1'][0].cpu().numpy(), c['cuda_topk1'].astype(np.int32))
+    np.testing.assert_array_equal(det['topk2'][0].cpu().numpy(), c['cuda_topk2'].astype(np.int32))
+    assert int(det['local_iters'][0]) == int(c['cuda_local_iters'])
+    fit_gpu, fit_ref = fit[0].cpu().numpy(), c['cuda_fitness']
+    assert np.abs(fit_gpu - fit_ref).max() <= 2 and (fit_gpu != fit_ref).mean() < 0.02
+    assert int(det['best_seed'][0]) == int(c['cuda_best_seed'])
+    _pose_close(T[0].cpu().numpy(), c['cuda_final_trans'])
+    assert int((labels[0].cpu().numpy() != c['cuda_labels']).sum()) == 0
 
 
 def test_batched_equals_loop(golden_dir):
