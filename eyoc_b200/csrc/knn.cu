@@ -59,7 +59,8 @@ __device__ __forceinline__ float value_of(float a) {
 template <int FORM>
 __global__ void __launch_bounds__(NTHREADS, 2)
 knn1_kernel(const float* __restrict__ Q, const float* __restrict__ R, int nq, int nr, int dim, int dimp,
-            int tiles_per_split, unsigned long long* __restrict__ keys, const int* __restrict__ only_if) {
+            int tiles_per_split, unsigned long long* __restrict__ keys, const int* __restrict__ only_if,
+            const int64_t* __restrict__ exclude) {
     extern __shared__ float smem[];
     float* Qs = smem;                 // [dimp][TQ]
     float* Rs = smem + dimp * TQ;     // [TC][TR]
@@ -72,6 +73,13 @@ knn1_kernel(const float* __restrict__ Q, const float* __restrict__ R, int nq, in
     const int tx = tid & 15, ty = tid >> 4;
     const int q0 = blockIdx.x * TQ;
     const bool vec_ok = (dim % 4 == 0);
+    // second-nearest pass (eyoc_knn1_excluding): the reference column each query row must ignore
+    int excl[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int q = q0 + ty * 8 + i;
+        excl[i] = (exclude != nullptr && q < nq) ? (int)exclude[(size_t)b * nq + q] : -1;
+    }
 
     // stage the whole query tile (all channel chunks), transposed to c-major
     for (int r = warp * 32 + lane; r < TQ; r += NTHREADS) {
@@ -166,7 +174,7 @@ knn1_kernel(const float* __restrict__ Q, const float* __restrict__ R, int nq, in
         for (int j = 0; j < 8; ++j)
 #pragma unroll
             for (int i = 0; i < 8; ++i) any |= (FORM == 1) ? !(acc[i][j] <= best[i]) : !(acc[i][j] >= best[i]);
-        if (firstj < 0) {
+        if (firstj < 0 && exclude == nullptr) {
 #pragma unroll
             for (int j = 7; j >= 0; --j) {
                 const int col = r0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
@@ -181,7 +189,7 @@ knn1_kernel(const float* __restrict__ Q, const float* __restrict__ R, int nq, in
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float a = acc[i][j];
-                        const bool maybe = (FORM == 1) ? !(a <= best[i]) : !(a >= best[i]);
+                        const bool maybe = ((FORM == 1) ? !(a <= best[i]) : !(a >= best[i])) && col != excl[i];
                         if (maybe) {
                             const float v = value_of<FORM>(a), bv = value_of<FORM>(best[i]);
                             const bool take = (v < bv) || (v != v && bv == bv);
@@ -217,6 +225,11 @@ __global__ void knn1_decode_kernel(const unsigned long long* __restrict__ keys, 
     if (i >= n) return;
     const unsigned long long k = keys[i];
     const unsigned int enc = (unsigned int)(k >> 32);
+    if (k == 0xffffffffffffffffull) {          // no admissible column (eyoc_knn1_excluding on a one-column reference set)
+        if (idx) idx[i] = -1;
+        if (dist) dist[i] = __int_as_float(0x7f800000);
+        return;
+    }
     if (idx) idx[i] = (int64_t)(unsigned int)(k & 0xffffffffu);
     if (dist) dist[i] = enc == 0u ? __int_as_float(0x7fc00000) : __uint_as_float(enc - 1u);
 }
@@ -497,7 +510,7 @@ knn_tc_kernel(const float* __restrict__ Q, const float* __restrict__ R, const ui
 
 // the fp32-FMA kernel over all batches (only_if == NULL) or over the batches whose only_if[b] != 0
 static int launch_ffma(const float* q, const float* r, int batch, int64_t nq, int64_t nr, int dim, int form,
-                       unsigned long long* keys, const int* only_if, cudaStream_t stream) {
+                       unsigned long long* keys, const int* only_if, cudaStream_t stream, const int64_t* exclude = nullptr) {
     const int dimp = (dim + TC - 1) / TC * TC;
     const int qtiles = (int)((nq + TQ - 1) / TQ);
     const int rtiles = (int)((nr + TR - 1) / TR);
@@ -509,10 +522,10 @@ static int launch_ffma(const float* q, const float* r, int batch, int64_t nq, in
     dim3 grid(qtiles, nsplit, batch);
     if (form == 0) {
         EYOC_CUDA(cudaFuncSetAttribute(knn1_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn1_kernel<0><<<grid, NTHREADS, smem, stream>>>(q, r, (int)nq, (int)nr, dim, dimp, tiles_per_split, keys, only_if);
+        knn1_kernel<0><<<grid, NTHREADS, smem, stream>>>(q, r, (int)nq, (int)nr, dim, dimp, tiles_per_split, keys, only_if, exclude);
     } else {
         EYOC_CUDA(cudaFuncSetAttribute(knn1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn1_kernel<1><<<grid, NTHREADS, smem, stream>>>(q, r, (int)nq, (int)nr, dim, dimp, tiles_per_split, keys, only_if);
+        knn1_kernel<1><<<grid, NTHREADS, smem, stream>>>(q, r, (int)nq, (int)nr, dim, dimp, tiles_per_split, keys, only_if, exclude);
     }
     EYOC_LAUNCH_CHECK();
     return EYOC_OK;
@@ -545,6 +558,33 @@ extern "C" int eyoc_knn1(const float* q, const float* r, int batch, int64_t nq, 
         const int rc = launch_ffma(q, r, batch, nq, nr, dim, form, keys, nullptr, stream);
         if (rc != EYOC_OK) return rc;
     }
+    const int64_t n = (int64_t)batch * nq;
+    knn1_decode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(keys, n, idx, dist);
+    EYOC_LAUNCH_CHECK();
+    return EYOC_OK;
+}
+
+// Nearest neighbour EXCLUDING one reference column per query (exclude [batch, nq] int64): the second pass of a K = 2
+// search (pytorch3d.ops.knn_points(K=2) in lib/trainer.py:1064-1065: squared distances, ascending, ties by lowest index).
+// Rows whose reference set has nothing but the excluded column get idx = -1 / dist = +inf.
+extern "C" int eyoc_knn1_excluding(const float* q, const float* r, int batch, int64_t nq, int64_t nr, int dim, int form,
+                                   const int64_t* exclude, void* workspace, size_t workspace_bytes, int64_t* idx, float* dist,
+                                   cudaStream_t stream) {
+    EYOC_CHECK_ARG(q && r && exclude, "eyoc_knn1_excluding: null pointer");
+    EYOC_CHECK_ARG(batch >= 1 && nq >= 0 && dim >= 1 && dim <= 256, "eyoc_knn1_excluding: bad shape batch=%d nq=%lld dim=%d", batch,
+                   (long long)nq, dim);
+    EYOC_CHECK_ARG(form == 0 || form == 1, "eyoc_knn1_excluding: form must be 0 or 1");
+    EYOC_CHECK_ARG(nq < (1ll << 31) && nr < (1ll << 31) && nr >= 1, "eyoc_knn1_excluding: bad sizes");
+    EYOC_CHECK_ARG(idx || dist, "eyoc_knn1_excluding: no output requested");
+    if (nq == 0) return EYOC_OK;
+    if (workspace == nullptr || workspace_bytes < eyoc_knn1_workspace_bytes(batch, nq)) {
+        eyoc_set_error("eyoc_knn1_excluding: workspace too small (%zu < %zu)", workspace_bytes, eyoc_knn1_workspace_bytes(batch, nq));
+        return EYOC_ERR_WORKSPACE;
+    }
+    unsigned long long* keys = (unsigned long long*)workspace;
+    EYOC_CUDA(cudaMemsetAsync(keys, 0xff, (size_t)batch * nq * sizeof(unsigned long long), stream));
+    const int rc = launch_ffma(q, r, batch, nq, nr, dim, form, keys, nullptr, stream, exclude);
+    if (rc != EYOC_OK) return rc;
     const int64_t n = (int64_t)batch * nq;
     knn1_decode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(keys, n, idx, dist);
     EYOC_LAUNCH_CHECK();

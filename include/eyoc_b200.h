@@ -41,6 +41,12 @@ unsigned long long eyoc_launch_count(void);
 size_t eyoc_knn1_workspace_bytes(int batch, int64_t nq);
 int eyoc_knn1(const float* q, const float* r, int batch, int64_t nq, int64_t nr, int dim, int form,
               void* workspace, size_t workspace_bytes, int64_t* idx, float* dist, eyoc_stream_t stream);
+/* Nearest neighbour ignoring one reference column per query (exclude [batch, nq] int64): second pass of the K = 2 search
+ * of lib/trainer.py:1064-1065 (pytorch3d.ops.knn_points: squared L2, ascending, ties by lowest index).  A query whose
+ * reference set holds nothing but the excluded column gets idx -1 / dist +inf.  Workspace: eyoc_knn1_workspace_bytes. */
+int eyoc_knn1_excluding(const float* q, const float* r, int batch, int64_t nq, int64_t nr, int dim, int form,
+                        const int64_t* exclude, void* workspace, size_t workspace_bytes, int64_t* idx, float* dist,
+                        eyoc_stream_t stream);
 /* The same operator for 32-channel descriptors with a tensor-core pre-filter: fp16 scores on tcgen05 with a rigorous
  * error bound select the few columns per row that can be the exact winner; those are re-scored in eyoc_knn1's fp32-FMA
  * order, so idx / dist are bit-identical to eyoc_knn1's.  Batches holding non-finite or fp16-overflowing values are

@@ -211,14 +211,14 @@ def test_range_guard_falls_back_to_fp32_activations():
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter('always')
         got = model(x).F.cpu()
-    assert any('fp16 hi/lo range' in str(m.message) for m in w)
+    assert any('fp16 hi/lo range' in str(m.message) for m in w), [str(m.message) for m in w]
     assert enn.CONV_MODE == 'f16x3'                                   # restored
-    assert bool(torch.isfinite(got).all())
-    assert float((got - want).abs().max()) <= 2e-5, float((got - want).abs().max())
+    assert bool(torch.isfinite(got).all()), 'fallback output not finite'
+    assert float((got - want).abs().max()) <= 5e-5, ('fallback vs oracle', float((got - want).abs().max()))
     # without the guard the same forward is not finite (this is what the flag protects against)
     model.RANGE_CHECK = False
     raw = model(SparseTensor(feats.cuda(), coordinates=torch.from_numpy(coords).cuda())).F
-    assert not bool(torch.isfinite(raw).all())
+    assert not bool(torch.isfinite(raw).all()), 'the unguarded split-half forward was expected to overflow'
     # in-range weights: no flag, no warning
     sd2 = RO.make_state_dict(1, 32, 5, seed=8)
     model.load_state_dict(sd2)
@@ -227,4 +227,5 @@ def test_range_guard_falls_back_to_fp32_activations():
     with warnings.catch_warnings(record=True) as w2:
         warnings.simplefilter('always')
         model(x2)
-    assert not w2 and int(x2.coordinate_manager.range_status.item()) == 0
+    assert not w2, [str(m.message) for m in w2]
+    assert int(x2.coordinate_manager.range_status.item()) == 0
