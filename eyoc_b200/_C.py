@@ -34,7 +34,7 @@ class SC2Layout(ctypes.Structure):
                                         'topk1', 'topk2', 'local_v', 'seed_weights', 'seed_trans', 'counters',
                                         'global_iters', 'local_notclose', 'best_seed', 'refine_counts', 'total',
                                         'csr_rowptr', 'csr_cols', 'csr_vals', 'csr_capacity', 'sort_keys', 'sort_idx',
-                                        'sort_offsets', 'sort_temp', 'sort_temp_bytes', 'near_bits', 'status')] + \
+                                        'sort_offsets', 'sort_temp', 'sort_temp_bytes', 'near_bits', 'status', 'big')] + \
                [(k, c_int) for k in ('words_per_row', 'k1', 'k2', 'num_seeds')]
 
 

@@ -71,75 +71,136 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
     return x;
 }
 
-// grid (ceil(n/32), batch); lane = row, the 8 warps split the 32-bit words of each 1024-column tile.
-// cross_dist(i, j) == cross_dist(j, i) bit for bit ((a-b)^2 == (b-a)^2), so only the 32x32 bit blocks on and above the
-// diagonal are evaluated; the mirrored block is the bit transpose (shuffle butterfly).
-// Three bit matrices: hard (cross < d), tight (cross < d/2), near (||s_i - s_j|| < R, the NMS neighbourhood of pick_seeds,
-// SC2_PCR.py:50: "dist >= R" <=> "sum of squares >= s0", see sqrt_threshold).
-// The two correctly rounded square roots of cross_dist are only needed near a threshold: MUFU approximations (relative
-// error <= 2^-23, PTX ISA) first, and the exact evaluation for the whole warp step only when some lane's approximate value
-// lies within the error margin of d or d/2.  The margin 2^-20 (ds + dt) is > 4x the worst-case difference between the
-// approximate and the exactly rounded |ds - dt| ((2^-23 + 2^-24)(ds + dt) + 2^-24 |ds - dt|), so the bits are those of the
-// exact evaluation (tests/test_sc2pcr_gpu.py::test_first_order_bits_bit_exact).
-__global__ void __launch_bounds__(256)
+// Packed fp32 pairs (sm_100 add / sub / mul / fma .f32x2): two independent round-to-nearest fp32 operations per instruction,
+// every result bit that of the scalar instruction.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
+// First-order compatibility as three bit matrices (row stride W words, W a multiple of 4):
+//   hard (cross < d), tight (cross < d/2), near (||s_i - s_j|| < R: the NMS neighbourhood of pick_seeds, SC2_PCR.py:50,
+//   "dist >= R" <=> "sum of squares >= s0", see sqrt_threshold).
+// cross_dist(i, j) == cross_dist(j, i) bit for bit ((a-b)^2 == (b-a)^2), so only macro tiles on and above the diagonal are
+// evaluated and the mirrored words are the bit transposes (shuffle butterfly).
+// Work decomposition: grid (ceil(n / 512), ceil(n / 128), batch), 4 warps; warp w owns the 128 x 128 macro tile
+// (A = blockIdx.y, B = 4 blockIdx.x + w), i.e. 4 x 4 blocks of 32 rows (lane = row) x 32 columns (one word).  Every store
+// is then a 16-byte piece of a row (4 consecutive words) - the one-word-per-row stores of a block-at-a-time scheme cost
+// a 32-byte sector for 4 useful bytes and made the LSU, not the ALU, the limiter.
+// Arithmetic: sums of squares on packed f32x2 (two columns per instruction).  The two correctly rounded square roots of
+// cross_dist are only needed near a threshold: MUFU approximations (relative error <= 2^-23, PTX ISA) first, and the exact
+// evaluation for the whole warp step only when some lane's approximate value lies within the error margin of d or d/2.
+// The margin 2^-20 (ds + dt) is > 3x the worst-case difference between the approximate and the exactly rounded |ds - dt|
+// ((2^-23 + 2^-24)(ds + dt) + 2^-24 |ds - dt|), so the bits are those of the exact evaluation
+// (tests/test_sc2pcr_gpu.py::test_first_order_bits_bit_exact, ..._near_threshold_stress).
+constexpr int FO_COLS = 512;
+__global__ void __launch_bounds__(128)
 first_order_bits_kernel(const Pt* __restrict__ P, int n, int W, float d_thre, float d_half, float near_s0,
                         uint32_t* __restrict__ hard, uint32_t* __restrict__ tight, uint32_t* __restrict__ near) {
-    __shared__ Pt tile[CT];
-    const int b = blockIdx.y;
+    __shared__ __align__(16) float cs[6][FO_COLS];          // column points, structure of arrays: sx sy sz tx ty tz
+    const int A = blockIdx.y;
+    if ((int)blockIdx.x * 4 + 3 < A) return;              // the whole CTA lies below the diagonal
+    const int b = blockIdx.z;
     P += (size_t)b * n;
     hard += (size_t)b * n * W;
     tight += (size_t)b * n * W;
     near += (size_t)b * n * W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int I = blockIdx.x;                        // 32-row block == word index of these rows
-    const int i = I * 32 + lane;
-    const bool row_ok = i < n;
-    Pt me = load_pt(P + min(i, n - 1));
-    for (int c0 = (I * 32 / CT) * CT; c0 < n; c0 += CT) {
-        __syncthreads();
-        for (int t = threadIdx.x; t < CT; t += 256) tile[t] = load_pt(P + min(c0 + t, n - 1));
-        __syncthreads();
-        for (int wl = warp; wl < (CT / 32); wl += 8) {
-            const int J = (c0 >> 5) + wl;            // word (32-column block) index
-            if (J * 32 >= n) break;
-            if (J < I) continue;                      // below the diagonal: written by the mirrored block
+    const int c_base = blockIdx.x * FO_COLS;
+    for (int t = threadIdx.x; t < FO_COLS; t += 128) {
+        const Pt q = load_pt(P + min(c_base + t, n - 1));
+        cs[0][t] = q.sx; cs[1][t] = q.sy; cs[2][t] = q.sz; cs[3][t] = q.tx; cs[4][t] = q.ty; cs[5][t] = q.tz;
+    }
+    __syncthreads();
+    const int B = blockIdx.x * 4 + warp;
+    if (B < A || B * 128 >= n) return;
+    const float* col = &cs[0][warp * 128];
+    uint32_t fh[4][4], ft[4][4], fn[4][4];
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) {
+        const int i = A * 128 + ri * 32 + lane;
+        const bool row_ok = i < n;
+        const Pt me = load_pt(P + min(i, n - 1));
+        const f32x2 mx = pack2(me.sx, me.sx), my = pack2(me.sy, me.sy), mz = pack2(me.sz, me.sz);
+        const f32x2 ux = pack2(me.tx, me.tx), uy = pack2(me.ty, me.ty), uz = pack2(me.tz, me.tz);
+#pragma unroll
+        for (int cj = 0; cj < 4; ++cj) {
+            if (A == B && cj < ri) {                      // diagonal macro tile: the mirror image of a block already evaluated
+                fh[ri][cj] = transpose32(fh[cj][ri], lane);
+                ft[ri][cj] = transpose32(ft[cj][ri], lane);
+                fn[ri][cj] = transpose32(fn[cj][ri], lane);
+                continue;
+            }
             uint32_t hb = 0, tb = 0, nb = 0;
+            const int j0 = B * 128 + cj * 32;
 #pragma unroll 4
-            for (int bit = 0; bit < 32; ++bit) {
-                const int j = J * 32 + bit;
-                const Pt q = tile[wl * 32 + bit];
-                float dx = __fsub_rn(me.sx, q.sx), dy = __fsub_rn(me.sy, q.sy), dz = __fsub_rn(me.sz, q.sz);
-                const float ss = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));      // dist3_fma's sum of squares
-                dx = __fsub_rn(me.tx, q.tx); dy = __fsub_rn(me.ty, q.ty); dz = __fsub_rn(me.tz, q.tz);
-                const float tt = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-                const float da = sqrt_approx(ss), db = sqrt_approx(tt);
-                const float ca = fabsf(da - db), mg = (da + db) * 9.5367431640625e-07f;      // 2^-20
-                bool h = ca < d_thre, t = ca < d_half;
-                const bool unsure = !(fabsf(ca - d_thre) > mg) || !(fabsf(ca - d_half) > mg);   // also true for NaN / Inf
+            for (int bp = 0; bp < 16; ++bp) {
+                const int c = cj * 32 + 2 * bp;
+                f32x2 dx = sub2(mx, *reinterpret_cast<const f32x2*>(col + c));
+                f32x2 dy = sub2(my, *reinterpret_cast<const f32x2*>(col + FO_COLS + c));
+                f32x2 dz = sub2(mz, *reinterpret_cast<const f32x2*>(col + 2 * FO_COLS + c));
+                const f32x2 ss2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));                 // dist3_fma's sum of squares
+                dx = sub2(ux, *reinterpret_cast<const f32x2*>(col + 3 * FO_COLS + c));
+                dy = sub2(uy, *reinterpret_cast<const f32x2*>(col + 4 * FO_COLS + c));
+                dz = sub2(uz, *reinterpret_cast<const f32x2*>(col + 5 * FO_COLS + c));
+                const f32x2 tt2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+                float ss[2], tt[2];
+                unpack2(ss2, ss[0], ss[1]);
+                unpack2(tt2, tt[0], tt[1]);
+                bool h[2], t[2], unsure = false;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float da = sqrt_approx(ss[e]), db = sqrt_approx(tt[e]);
+                    const float ca = fabsf(da - db), mg = (da + db) * 9.5367431640625e-07f;      // 2^-20
+                    h[e] = ca < d_thre;
+                    t[e] = ca < d_half;
+                    unsure |= !(fabsf(ca - d_thre) > mg) || !(fabsf(ca - d_half) > mg);          // also true for NaN / Inf
+                }
                 if (__any_sync(0xffffffffu, unsure)) {
-                    const float c = fabsf(__fsub_rn(__fsqrt_rn(ss), __fsqrt_rn(tt)));
-                    h = c < d_thre;
-                    t = c < d_half;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float cx = fabsf(__fsub_rn(__fsqrt_rn(ss[e]), __fsqrt_rn(tt[e])));
+                        h[e] = cx < d_thre;
+                        t[e] = cx < d_half;
+                    }
                 }
-                const bool ok = row_ok && j < n;
-                hb |= (uint32_t)(ok && h) << bit;
-                tb |= (uint32_t)(ok && t) << bit;
-                nb |= (uint32_t)(ok && !(ss >= near_s0)) << bit;
-            }
-            if (row_ok) {
-                hard[(size_t)i * W + J] = hb;
-                tight[(size_t)i * W + J] = tb;
-                near[(size_t)i * W + J] = nb;
-            }
-            if (J != I) {                             // warp-uniform
-                const uint32_t mh = transpose32(hb, lane), mt = transpose32(tb, lane), mn = transpose32(nb, lane);
-                const int jrow = J * 32 + lane;       // row J*32+lane, columns I*32 .. I*32+31
-                if (jrow < n) {
-                    hard[(size_t)jrow * W + I] = mh;
-                    tight[(size_t)jrow * W + I] = mt;
-                    near[(size_t)jrow * W + I] = mn;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const bool ok = row_ok && j0 + 2 * bp + e < n;
+                    hb |= (uint32_t)(ok && h[e]) << (2 * bp + e);
+                    tb |= (uint32_t)(ok && t[e]) << (2 * bp + e);
+                    nb |= (uint32_t)(ok && !(ss[e] >= near_s0)) << (2 * bp + e);
                 }
             }
+            fh[ri][cj] = hb; ft[ri][cj] = tb; fn[ri][cj] = nb;
+        }
+    }
+    // rows of macro row A, words 4 B .. 4 B + 3
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) {
+        const int i = A * 128 + ri * 32 + lane;
+        if (i < n) {
+            const size_t o = (size_t)i * W + 4 * B;
+            *reinterpret_cast<uint4*>(hard + o) = make_uint4(fh[ri][0], fh[ri][1], fh[ri][2], fh[ri][3]);
+            *reinterpret_cast<uint4*>(tight + o) = make_uint4(ft[ri][0], ft[ri][1], ft[ri][2], ft[ri][3]);
+            *reinterpret_cast<uint4*>(near + o) = make_uint4(fn[ri][0], fn[ri][1], fn[ri][2], fn[ri][3]);
+        }
+    }
+    if (A == B) return;
+    // mirrored: rows of macro row B, words 4 A .. 4 A + 3
+#pragma unroll
+    for (int cj = 0; cj < 4; ++cj) {
+        const uint4 mh = make_uint4(transpose32(fh[0][cj], lane), transpose32(fh[1][cj], lane), transpose32(fh[2][cj], lane), transpose32(fh[3][cj], lane));
+        const uint4 mt = make_uint4(transpose32(ft[0][cj], lane), transpose32(ft[1][cj], lane), transpose32(ft[2][cj], lane), transpose32(ft[3][cj], lane));
+        const uint4 mn = make_uint4(transpose32(fn[0][cj], lane), transpose32(fn[1][cj], lane), transpose32(fn[2][cj], lane), transpose32(fn[3][cj], lane));
+        const int jrow = B * 128 + cj * 32 + lane;
+        if (jrow < n) {
+            const size_t o = (size_t)jrow * W + 4 * A;
+            *reinterpret_cast<uint4*>(hard + o) = mh;
+            *reinterpret_cast<uint4*>(tight + o) = mt;
+            *reinterpret_cast<uint4*>(near + o) = mn;
         }
     }
 }
@@ -425,47 +486,61 @@ struct SeedArgs {
     int32_t* topk2;       // [batch, S, k2]
     float* local_v;       // [batch, S, num_iterations, MAXK]
     int* local_notclose;  // [batch, num_iterations + 1]
+    int keycap;           // candidate capacity of the first-tier launch (shared-memory keys)
+    int* big;             // [2 + batch * S]: number of deferred seeds | work cursor | their flat indices b * S + s
 };
 
-__global__ void __launch_bounds__(256)
-seed_consensus_kernel(SeedArgs a) {
-    extern __shared__ uint32_t sm[];
+// A seed's candidate columns are the set bits of its `hard` row - a few dozen on LiDAR data (0.4 % of the matrix), n at
+// most.  The kernel is bound by per-CTA latency chains, not by traffic, so what matters is how many seeds an SM works on at
+// once: 128-thread CTAs whose candidate keys take KEYCAP words of shared memory (16 CTAs per SM) handle every seed with
+// <= KEYCAP candidates; the rare denser ones are deferred to a second launch sized for n candidates.
+constexpr int SC_NT = 128;
+constexpr int SC_KEYCAP = 1024;
+
+// returns false (nothing written) when the seed has more candidates than `keycap`
+__device__ __forceinline__ bool seed_consensus_body(const SeedArgs& a, const int b, const int s, uint32_t* sm, const int keycap) {
     const int n = a.n, W = a.W;
     uint32_t* trow = sm;                 // [W]
     uint32_t* hrow = sm + W;             // [W]
     uint32_t* nzmap = sm + 2 * W;        // [W] columns with a non-zero SC2 value
-    uint32_t* keys = sm + 3 * W;         // [n]  (count << 16) | (65535 - j)
-    __shared__ int ncand, nnz, nwin;
-    __shared__ unsigned int hist[256], wtot[8], sel_bin, sel_rem;
+    uint32_t* keys = sm + 3 * W;         // [keycap]  (count << 16) | (65535 - j)
+    __shared__ int ncand, npos, nnz, nwin;
+    __shared__ unsigned int hist[256], sel_bin, sel_rem;
     __shared__ uint32_t win[MAXK];
     __shared__ int idx1[MAXK], idx2[MAXK], fine[MAXK], lval[MAXK];
     __shared__ uint32_t lhard[MAXK];
     __shared__ float ls[MAXK][3], lt[MAXK][3];
     __shared__ float M[MAXK][MAXK + 1];
 
-    const int b = blockIdx.y, s = blockIdx.x;
     const Pt* P = a.P + (size_t)b * n;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k1 = a.k1, k2 = a.k2;
 
-    if (tid == 0) { ncand = 0; nnz = 0; nwin = 0; }
-    for (int w = tid; w < W; w += 256) nzmap[w] = 0;
+    if (tid == 0) { ncand = 0; npos = 0; nnz = 0; nwin = 0; }
+    for (int w = tid; w < W; w += SC_NT) nzmap[w] = 0;
     __syncthreads();
     int nc;
     if (a.sc2_dense == nullptr) {
         const uint32_t* tight = a.tight + (size_t)b * n * W;
         const int seed = a.seeds[(size_t)b * a.S + s];
-        for (int w = tid; w < W; w += 256) {
+        int cnt = 0;
+        for (int w = tid; w < W; w += SC_NT) {
+            const uint32_t h = a.hard[((size_t)b * n + seed) * W + w];
             trow[w] = tight[(size_t)seed * W + w];
-            hrow[w] = a.hard[((size_t)b * n + seed) * W + w];
+            hrow[w] = h;
+            cnt += __popc(h);
         }
+        cnt = warp_sum_i(cnt);
+        if (lane == 0 && cnt) atomicAdd(&ncand, cnt);
         __syncthreads();
+        nc = ncand;
+        if (nc > keycap) return false;                    // CTA-uniform
         // 1. compact the columns where hard[seed] is set
-        for (int w = tid; w < W; w += 256) {
+        for (int w = tid; w < W; w += SC_NT) {
             uint32_t m = hrow[w];
             const int c = __popc(m);
             if (c) {
-                int pos = atomicAdd(&ncand, c);
+                int pos = atomicAdd(&npos, c);
                 while (m) {
                     const int bit = __ffs(m) - 1;
                     m &= m - 1;
@@ -474,18 +549,17 @@ seed_consensus_kernel(SeedArgs a) {
             }
         }
         __syncthreads();
-        nc = ncand;
         // 2. SC2[seed, j] = popc(tight[seed] & tight[j]) for those columns (warp per column)
         int nz = 0;
-        for (int c = warp; c < nc; c += 8) {
+        for (int c = warp; c < nc; c += SC_NT / 32) {
             const uint32_t jj = 65535u - keys[c];
             const uint32_t* row = tight + (size_t)jj * W;
-            int cnt = 0;
-            for (int w = lane; w < W; w += 32) cnt += __popc(trow[w] & __ldg(row + w));
-            cnt = warp_sum_i(cnt);
+            int cn = 0;
+            for (int w = lane; w < W; w += 32) cn += __popc(trow[w] & __ldg(row + w));
+            cn = warp_sum_i(cn);
             if (lane == 0) {
-                if (cnt > 0) {
-                    keys[c] = ((uint32_t)cnt << 16) | (65535u - jj);
+                if (cn > 0) {
+                    keys[c] = ((uint32_t)cn << 16) | (65535u - jj);
                     atomicOr(&nzmap[jj >> 5], 1u << (jj & 31));
                     ++nz;
                 } else {
@@ -496,15 +570,16 @@ seed_consensus_kernel(SeedArgs a) {
         if (lane == 0 && nz) atomicAdd(&nnz, nz);
     } else {
         // dense rows handed in by the caller: every column is a candidate; the values are the integer counts of SC2_PCR.py:363
+        if (n > keycap) return false;
         const float* row = a.sc2_dense + ((size_t)b * a.S + s) * n;
         nc = n;
         int nz = 0, bad = 0;
-        for (int j = tid; j < n; j += 256) {
+        for (int j = tid; j < n; j += SC_NT) {
             const float v = __ldg(row + j);
-            const int cnt = (int)v;
-            if (!(v >= 0.f && v <= 65535.f) || (float)cnt != v) bad = 1;
-            if (cnt > 0 && !bad) {
-                keys[j] = ((uint32_t)cnt << 16) | (65535u - (uint32_t)j);
+            const int cn = (int)v;
+            if (!(v >= 0.f && v <= 65535.f) || (float)cn != v) bad = 1;
+            if (cn > 0 && !bad) {
+                keys[j] = ((uint32_t)cn << 16) | (65535u - (uint32_t)j);
                 atomicOr(&nzmap[j >> 5], 1u << (j & 31));
                 ++nz;
             } else {
@@ -525,26 +600,30 @@ seed_consensus_kernel(SeedArgs a) {
         if (nnz > k1) {
 #pragma unroll 1
             for (int shift = 24; shift >= 0; shift -= 8) {
-                hist[tid] = 0;
+                for (int i = tid; i < 256; i += SC_NT) hist[i] = 0;
                 __syncthreads();
-                for (int c = tid; c < nc; c += 256) {
+                for (int c = tid; c < nc; c += SC_NT) {
                     const uint32_t key = keys[c];
                     if (key != 0u && (key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
                 }
                 __syncthreads();
-                // bin t is the one where the count of keys in higher bins first reaches `remaining`
-                const unsigned int h = hist[tid];
-                unsigned int incl = h;                      // inclusive suffix sum inside the warp (towards higher bins)
+                if (warp == 0) {          // the bin where the count of keys in higher bins first reaches `remaining`
+                    unsigned int h[8], tot = 0;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned int y = __shfl_down_sync(0xffffffffu, incl, o);
-                    if (lane + o < 32) incl += y;
+                    for (int k = 0; k < 8; ++k) { h[k] = hist[8 * lane + k]; tot += h[k]; }
+                    unsigned int incl = tot;              // inclusive suffix sum over the lanes (towards higher bins)
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned int y = __shfl_down_sync(0xffffffffu, incl, o);
+                        if (lane + o < 32) incl += y;
+                    }
+                    unsigned int above = incl - tot;
+#pragma unroll
+                    for (int k = 7; k >= 0; --k) {
+                        if (above < remaining && remaining <= above + h[k]) { sel_bin = (unsigned int)(8 * lane + k); sel_rem = remaining - above; }
+                        above += h[k];
+                    }
                 }
-                if (lane == 0) wtot[warp] = incl;
-                __syncthreads();
-                unsigned int above = incl - h;
-                for (int w2 = warp + 1; w2 < 8; ++w2) above += wtot[w2];
-                if (above < remaining && remaining <= above + h) { sel_bin = (unsigned int)tid; sel_rem = remaining - above; }
                 __syncthreads();
                 prefix |= sel_bin << shift;
                 pmask |= 255u << shift;
@@ -553,7 +632,7 @@ seed_consensus_kernel(SeedArgs a) {
         } else {
             prefix = 1u;                                    // every non-zero key wins
         }
-        for (int c = tid; c < nc; c += 256) {
+        for (int c = tid; c < nc; c += SC_NT) {
             const uint32_t key = keys[c];
             if (key != 0u && key >= prefix) win[atomicAdd(&nwin, 1)] = key;
         }
@@ -591,7 +670,7 @@ seed_consensus_kernel(SeedArgs a) {
     }
     __syncthreads();
     // 4. local hard compatibility among the k1 (SC2_PCR.py:94-100; ((a-b)**2).sum(-1)**0.5 form)
-    for (int e = tid; e < k1 * k1; e += 256) {
+    for (int e = tid; e < k1 * k1; e += SC_NT) {
         const int p = e / k1, q = e % k1;
         const float ds = dist3_sum(ls[p][0], ls[p][1], ls[p][2], ls[q][0], ls[q][1], ls[q][2]);
         const float dt = dist3_sum(lt[p][0], lt[p][1], lt[p][2], lt[q][0], lt[q][1], lt[q][2]);
@@ -616,9 +695,8 @@ seed_consensus_kernel(SeedArgs a) {
         idx2[tid] = idx1[fine[tid]];
         a.topk2[((size_t)b * a.S + s) * k2 + tid] = idx2[tid];
     }
-    __syncthreads();
     // 5. soft measure on the k2 (SC2_PCR.py:117-131), diagonal zeroed
-    for (int e = tid; e < k2 * k2; e += 256) {
+    for (int e = tid; e < k2 * k2; e += SC_NT) {
         const int p = e / k2, q = e % k2;
         const int fp = fine[p], fq = fine[q];
         const float ds = dist3_sum(ls[fp][0], ls[fp][1], ls[fp][2], ls[fq][0], ls[fq][1], ls[fq][2]);
@@ -628,25 +706,54 @@ seed_consensus_kernel(SeedArgs a) {
         M[p][q] = (p == q) ? 0.f : v;
     }
     __syncthreads();
-    // 6. power iteration on the k2 x k2 matrix by one warp; every iterate is kept
+    // 6. power iteration on the k2 x k2 matrix by one warp, the lane's matrix row in registers; every iterate is kept
     if (warp == 0) {
+        float mrow[MAXK];
+#pragma unroll
+        for (int q = 0; q < MAXK; ++q) mrow[q] = (lane < k2 && q < k2) ? M[lane][q] : 0.f;
         float v = 1.0f;
         float* out = a.local_v + ((size_t)b * a.S + s) * a.num_iterations * MAXK;
+        int* notclose = a.local_notclose + (size_t)b * (a.num_iterations + 1);
         for (int t = 1; t <= a.num_iterations; ++t) {
             float uu = 0.f;
-            for (int q = 0; q < k2; ++q) {
+#pragma unroll
+            for (int q = 0; q < MAXK; ++q) {
                 const float vq = __shfl_sync(0xffffffffu, v, q);
-                if (lane < k2) uu = __fmaf_rn(M[lane][q], vq, uu);
+                if (q < k2) uu = __fmaf_rn(mrow[q], vq, uu);              // rows >= k2 hold zeros
             }
             const float ss = warp_sum(lane < k2 ? __fmul_rn(uu, uu) : 0.f);
             const float vn = __fdiv_rn(uu, __fadd_rn(__fsqrt_rn(ss), 1e-6f));
             const float allowed = __fadd_rn(1e-8f, fabsf(__fmul_rn(1e-5f, v)));
             const bool close = (lane >= k2) || (fabsf(__fsub_rn(vn, v)) <= allowed);
-            if (!__all_sync(0xffffffffu, close) && lane == 0)
-                atomicAdd(a.local_notclose + (size_t)b * (a.num_iterations + 1) + t, 1);
+            if (!__all_sync(0xffffffffu, close) && lane == 0) atomicAdd(notclose + t, 1);
             if (lane < k2) out[(size_t)(t - 1) * MAXK + lane] = vn;
             v = vn;
         }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(SC_NT)
+seed_consensus_kernel(SeedArgs a) {
+    extern __shared__ uint32_t sm[];
+    const int b = blockIdx.y, s = blockIdx.x;
+    if (!seed_consensus_body(a, b, s, sm, a.keycap) && threadIdx.x == 0) a.big[2 + atomicAdd(a.big, 1)] = b * a.S + s;
+}
+
+// second tier: the deferred seeds (more than SC_KEYCAP candidates), keys sized for n; persistent CTAs walk the list
+__global__ void __launch_bounds__(SC_NT)
+seed_consensus_big_kernel(SeedArgs a) {
+    extern __shared__ uint32_t sm[];
+    __shared__ int item;
+    const int total = a.big[0];
+    for (;;) {
+        __syncthreads();                      // the previous seed's shared state is no longer read
+        if (threadIdx.x == 0) item = atomicAdd(a.big + 1, 1);
+        __syncthreads();
+        const int it = item;
+        if (it >= total) break;
+        const int g = a.big[2 + it];
+        seed_consensus_body(a, g / a.S, g % a.S, sm, a.n);
     }
 }
 
@@ -1052,7 +1159,7 @@ extern "C" int eyoc_sc2pcr_layout(int batch, int n, int num_seeds, const eyoc_sc
     int k1, k2;
     effective_k(cfg, n, &k1, &k2);
     const size_t B = batch, N = n, S = num_seeds, I = cfg->num_iterations;
-    const size_t W = (N + 31) / 32;
+    const size_t W = ((N + 31) / 32 + 3) / 4 * 4;          // words per bit row, padded to 16 bytes (first_order_bits_kernel)
     WsCarver c(nullptr, 0);
     L->points = c.off; c.take<Pt>(B * N);
     L->hard_bits = c.off; c.take<uint32_t>(B * N * W);
@@ -1092,6 +1199,7 @@ extern "C" int eyoc_sc2pcr_layout(int batch, int n, int num_seeds, const eyoc_sc
     L->best_seed = c.off; c.take<int>(B);
     L->refine_counts = c.off; c.take<int>(B * (cfg->refine_iterations + 1) + B * 16);   // counts | initial_trans (float)
     L->status = c.off; c.take<int>(4);
+    L->big = c.off; c.take<int>(2 + B * S);          // deferred seeds of seed_consensus (count | cursor | list)
     L->total = c.off;
     L->words_per_row = (int)W;
     L->k1 = k1;
@@ -1165,8 +1273,8 @@ extern "C" int eyoc_sc2pcr(const float* src, const float* tgt, int batch, int n,
     EYOC_CHECK_ARG(!sc2_dense || (hooks->seeds && !hooks->initial_trans), "eyoc_sc2pcr: the sc2_dense hook needs the seeds hook");
     if (!skip_seed_stage) {
         if (!sc2_dense) {       // dense SC2 rows + seeds from the caller: the bit matrices are not needed
-            first_order_bits_kernel<<<dim3((n + 31) / 32, batch), 256, 0, stream>>>(P, n, W, cfg->d_thre, cfg->d_thre_half,
-                                                                                  sqrt_threshold(cfg->nms_radius), hard, tight, near);
+            first_order_bits_kernel<<<dim3((n + FO_COLS - 1) / FO_COLS, (n + 127) / 128, batch), 128, 0, stream>>>(
+                P, n, W, cfg->d_thre, cfg->d_thre_half, sqrt_threshold(cfg->nms_radius), hard, tight, near);
             EYOC_LAUNCH_CHECK();
         }
         const float* conf_use = conf;
@@ -1194,12 +1302,19 @@ extern "C" int eyoc_sc2pcr(const float* src, const float* tgt, int batch, int n,
             rc = rank_seeds(ws, L, scores, batch, n, S, seeds, nullptr, stream);
             if (rc != EYOC_OK) return rc;
         }
+        const int keycap = sc2_dense ? n : (n < SC_KEYCAP ? n : SC_KEYCAP);
         SeedArgs sa{P, hard, tight, seeds_use, sc2_dense, status, n, W, S, L.k1, L.k2, I, cfg->d_thre, cfg->d_thre_sq, topk1, topk2,
-                    local_v, local_notclose};
-        const size_t smem = (size_t)(3 * W + n) * sizeof(uint32_t);
+                    local_v, local_notclose, keycap, (int*)(ws + L.big)};
+        const size_t smem = (size_t)(3 * W + keycap) * sizeof(uint32_t);
         EYOC_CUDA(cudaFuncSetAttribute(seed_consensus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        seed_consensus_kernel<<<dim3(S, batch), 256, smem, stream>>>(sa);
+        seed_consensus_kernel<<<dim3(S, batch), SC_NT, smem, stream>>>(sa);
         EYOC_LAUNCH_CHECK();
+        if (keycap < n) {                      // seeds with more than keycap candidates (none on typical data): exits at once
+            const size_t smem_big = (size_t)(3 * W + n) * sizeof(uint32_t);
+            EYOC_CUDA(cudaFuncSetAttribute(seed_consensus_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
+            seed_consensus_big_kernel<<<296, SC_NT, smem_big, stream>>>(sa);
+            EYOC_LAUNCH_CHECK();
+        }
         FitArgs fa{P, topk2, local_v, local_notclose, n, S, L.k2, I, cfg->inlier_threshold, seed_weights, seed_trans,
                    fitness ? fitness : scores /* scratch */, local_iters};
         if (!fitness) {

@@ -90,7 +90,7 @@ typedef struct {
     size_t points, hard_bits, tight_bits, vbuf, u, confidence, scores, seeds, topk1, topk2, local_v,
         seed_weights, seed_trans, counters, global_iters, local_notclose, best_seed, refine_counts, total,
         csr_rowptr, csr_cols, csr_vals, csr_capacity, sort_keys, sort_idx, sort_offsets, sort_temp, sort_temp_bytes,
-        near_bits, status;
+        near_bits, status, big;
     int words_per_row, k1, k2, num_seeds;
 } eyoc_sc2_layout;
 

@@ -150,7 +150,9 @@ def test_matcher_stage_methods(golden_dir, name):
     m = _matcher(cfg)
     ocfg = _ocfg(cfg, stable_ties=True)
     det = {}
-    O.sc2_pcr(src.cpu().clone(), tgt.cpu().clone(), ocfg, det)
+    # the oracle run HERE (its MKL power iteration can order near-equal confidences differently on another host CPU than
+    # the one that wrote the goldens): cal_seed_trans is compared with this run's own seeds / SC2 / fitness
+    _, fit_or = O.sc2_pcr(src.cpu().clone(), tgt.cpu().clone(), ocfg, det)
     src_dist, cross, SC, hard, tight = O.first_order(src.cpu(), tgt.cpu(), ocfg)
     n = src.shape[1]
     S = int(n * cfg['ratio'])
@@ -174,8 +176,8 @@ def test_matcher_stage_methods(golden_dir, name):
     assert torch.equal(seeds.cpu(), O.pick_seeds(src_dist, conf_ref, cfg['nms_radius'], S, stable=True))
     # cal_seed_trans on the oracle's dense second-order measure
     T0, fit = m.cal_seed_trans(det['seeds'].cuda(), det['SC2'].cuda(), src, tgt)
-    _pose_close(T0[0].cpu().numpy(), g['st_initial_trans'])
-    fit_gpu, fit_ref = fit[0].cpu().numpy(), g['st_fitness']
+    _pose_close(T0[0].cpu().numpy(), det['initial_trans'][0].numpy())
+    fit_gpu, fit_ref = fit[0].cpu().numpy(), fit_or[0].numpy()
     assert np.abs(fit_gpu - fit_ref).max() <= 2 and (fit_gpu != fit_ref).mean() < 0.02
     T0b, fitb, _ = m._run(src, tgt, want_labels=False, refine_iterations=0, hooks=dict(seeds=det['seeds']))
     assert torch.equal(T0, T0b) and torch.equal(fit, fitb)        # dense-SC2 route == bit-matrix route
