@@ -96,10 +96,19 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm(
 // ((2^-23 + 2^-24)(ds + dt) + 2^-24 |ds - dt|), so the bits are those of the exact evaluation
 // (tests/test_sc2pcr_gpu.py::test_first_order_bits_bit_exact, ..._near_threshold_stress).
 constexpr int FO_COLS = 512;
+
+// exact classification of one entry (kept out of line: it runs for a handful of warp steps per million, and inlining it
+// into every unrolled copy of the inner loop made the kernel instruction-fetch bound)
+__device__ __noinline__ uint32_t first_order_exact(float ss, float tt, float d_thre, float d_half) {
+    const float c = fabsf(__fsub_rn(__fsqrt_rn(ss), __fsqrt_rn(tt)));
+    return (uint32_t)(c < d_thre) | ((uint32_t)(c < d_half) << 1);
+}
+
 __global__ void __launch_bounds__(128)
 first_order_bits_kernel(const Pt* __restrict__ P, int n, int W, float d_thre, float d_half, float near_s0,
                         uint32_t* __restrict__ hard, uint32_t* __restrict__ tight, uint32_t* __restrict__ near) {
     __shared__ __align__(16) float cs[6][FO_COLS];          // column points, structure of arrays: sx sy sz tx ty tz
+    __shared__ uint32_t blk[4][3][16][32];                  // per warp: the 16 block results (hard | tight | near) x lane
     const int A = blockIdx.y;
     if ((int)blockIdx.x * 4 + 3 < A) return;              // the whole CTA lies below the diagonal
     const int b = blockIdx.z;
@@ -117,22 +126,16 @@ first_order_bits_kernel(const Pt* __restrict__ P, int n, int W, float d_thre, fl
     const int B = blockIdx.x * 4 + warp;
     if (B < A || B * 128 >= n) return;
     const float* col = &cs[0][warp * 128];
-    uint32_t fh[4][4], ft[4][4], fn[4][4];
-#pragma unroll
+    uint32_t (*res)[16][32] = blk[warp];
+#pragma unroll 1
     for (int ri = 0; ri < 4; ++ri) {
         const int i = A * 128 + ri * 32 + lane;
         const bool row_ok = i < n;
         const Pt me = load_pt(P + min(i, n - 1));
         const f32x2 mx = pack2(me.sx, me.sx), my = pack2(me.sy, me.sy), mz = pack2(me.sz, me.sz);
         const f32x2 ux = pack2(me.tx, me.tx), uy = pack2(me.ty, me.ty), uz = pack2(me.tz, me.tz);
-#pragma unroll
-        for (int cj = 0; cj < 4; ++cj) {
-            if (A == B && cj < ri) {                      // diagonal macro tile: the mirror image of a block already evaluated
-                fh[ri][cj] = transpose32(fh[cj][ri], lane);
-                ft[ri][cj] = transpose32(ft[cj][ri], lane);
-                fn[ri][cj] = transpose32(fn[cj][ri], lane);
-                continue;
-            }
+#pragma unroll 1
+        for (int cj = (A == B ? ri : 0); cj < 4; ++cj) {   // diagonal macro tile: blocks below its diagonal are mirror images
             uint32_t hb = 0, tb = 0, nb = 0;
             const int j0 = B * 128 + cj * 32;
 #pragma unroll 4
@@ -149,58 +152,64 @@ first_order_bits_kernel(const Pt* __restrict__ P, int n, int W, float d_thre, fl
                 float ss[2], tt[2];
                 unpack2(ss2, ss[0], ss[1]);
                 unpack2(tt2, tt[0], tt[1]);
-                bool h[2], t[2], unsure = false;
+                uint32_t ht[2];
+                bool unsure = false;
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const float da = sqrt_approx(ss[e]), db = sqrt_approx(tt[e]);
                     const float ca = fabsf(da - db), mg = (da + db) * 9.5367431640625e-07f;      // 2^-20
-                    h[e] = ca < d_thre;
-                    t[e] = ca < d_half;
+                    ht[e] = (uint32_t)(ca < d_thre) | ((uint32_t)(ca < d_half) << 1);
                     unsure |= !(fabsf(ca - d_thre) > mg) || !(fabsf(ca - d_half) > mg);          // also true for NaN / Inf
                 }
                 if (__any_sync(0xffffffffu, unsure)) {
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const float cx = fabsf(__fsub_rn(__fsqrt_rn(ss[e]), __fsqrt_rn(tt[e])));
-                        h[e] = cx < d_thre;
-                        t[e] = cx < d_half;
-                    }
+                    ht[0] = first_order_exact(ss[0], tt[0], d_thre, d_half);
+                    ht[1] = first_order_exact(ss[1], tt[1], d_thre, d_half);
                 }
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const bool ok = row_ok && j0 + 2 * bp + e < n;
-                    hb |= (uint32_t)(ok && h[e]) << (2 * bp + e);
-                    tb |= (uint32_t)(ok && t[e]) << (2 * bp + e);
-                    nb |= (uint32_t)(ok && !(ss[e] >= near_s0)) << (2 * bp + e);
+                    const uint32_t ok = (row_ok && j0 + 2 * bp + e < n) ? 1u : 0u;
+                    hb |= (ht[e] & ok) << (2 * bp + e);
+                    tb |= ((ht[e] >> 1) & ok) << (2 * bp + e);
+                    nb |= ((uint32_t)(!(ss[e] >= near_s0)) & ok) << (2 * bp + e);
                 }
             }
-            fh[ri][cj] = hb; ft[ri][cj] = tb; fn[ri][cj] = nb;
+            res[0][ri * 4 + cj][lane] = hb;
+            res[1][ri * 4 + cj][lane] = tb;
+            res[2][ri * 4 + cj][lane] = nb;
         }
     }
+    __syncwarp();
+    if (A == B) {
+#pragma unroll 1
+        for (int m = 0; m < 3; ++m)
+#pragma unroll 1
+            for (int ri = 1; ri < 4; ++ri)
+                for (int cj = 0; cj < ri; ++cj) res[m][ri * 4 + cj][lane] = transpose32(res[m][cj * 4 + ri][lane], lane);
+        __syncwarp();
+    }
+    uint32_t* const mats[3] = {hard, tight, near};
     // rows of macro row A, words 4 B .. 4 B + 3
-#pragma unroll
+#pragma unroll 1
     for (int ri = 0; ri < 4; ++ri) {
         const int i = A * 128 + ri * 32 + lane;
         if (i < n) {
             const size_t o = (size_t)i * W + 4 * B;
-            *reinterpret_cast<uint4*>(hard + o) = make_uint4(fh[ri][0], fh[ri][1], fh[ri][2], fh[ri][3]);
-            *reinterpret_cast<uint4*>(tight + o) = make_uint4(ft[ri][0], ft[ri][1], ft[ri][2], ft[ri][3]);
-            *reinterpret_cast<uint4*>(near + o) = make_uint4(fn[ri][0], fn[ri][1], fn[ri][2], fn[ri][3]);
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+                *reinterpret_cast<uint4*>(mats[m] + o) =
+                    make_uint4(res[m][ri * 4][lane], res[m][ri * 4 + 1][lane], res[m][ri * 4 + 2][lane], res[m][ri * 4 + 3][lane]);
         }
     }
     if (A == B) return;
     // mirrored: rows of macro row B, words 4 A .. 4 A + 3
-#pragma unroll
+#pragma unroll 1
     for (int cj = 0; cj < 4; ++cj) {
-        const uint4 mh = make_uint4(transpose32(fh[0][cj], lane), transpose32(fh[1][cj], lane), transpose32(fh[2][cj], lane), transpose32(fh[3][cj], lane));
-        const uint4 mt = make_uint4(transpose32(ft[0][cj], lane), transpose32(ft[1][cj], lane), transpose32(ft[2][cj], lane), transpose32(ft[3][cj], lane));
-        const uint4 mn = make_uint4(transpose32(fn[0][cj], lane), transpose32(fn[1][cj], lane), transpose32(fn[2][cj], lane), transpose32(fn[3][cj], lane));
         const int jrow = B * 128 + cj * 32 + lane;
-        if (jrow < n) {
-            const size_t o = (size_t)jrow * W + 4 * A;
-            *reinterpret_cast<uint4*>(hard + o) = mh;
-            *reinterpret_cast<uint4*>(tight + o) = mt;
-            *reinterpret_cast<uint4*>(near + o) = mn;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            const uint4 v = make_uint4(transpose32(res[m][cj][lane], lane), transpose32(res[m][4 + cj][lane], lane),
+                                       transpose32(res[m][8 + cj][lane], lane), transpose32(res[m][12 + cj][lane], lane));
+            if (jrow < n) *reinterpret_cast<uint4*>(mats[m] + (size_t)jrow * W + 4 * A) = v;
         }
     }
 }
