@@ -187,7 +187,8 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from eyoc_b200 import _C, nn as enn, synth
-    from eyoc_b200.pipeline import PlanPrefetcher, RegistrationPipeline, gather_records, plan_to_device
+    from eyoc_b200.pipeline import (AsyncRecords, BlockUploader, PlanPrefetcher, RegistrationPipeline, gather_records,
+                                    plan_to_device)
     from eyoc_b200.scripts.SC2_PCR.SC2_PCR import Matcher
     from eyoc_b200.scripts.test_kitti import is_success, rte_rre
 
@@ -231,17 +232,32 @@ def run_ours(args):
         rec = pipe.records(out, list(range(rank * P, rank * P + P)))
         return gather_records(rec, P * world), out
 
+    # End to end: host inputs every step.  The copies of block i + 1 (coordinates, points, the freshly drawn index plan) run on
+    # a copy stream while block i computes; the all-gather and the device-to-host read of block i's records run on side
+    # streams and are collected by the host one block later - the compute stream never waits for a copy or a collective.
     prefetch = None
+    uploader = BlockUploader(dev)
+    rec_hosts = [torch.empty((P * world, 24), dtype=torch.float32).pin_memory() for _ in range(2)]
+    ids = list(range(rank * P, rank * P + P))
 
-    def step_e2e():
-        c = coords_h.to(dev, non_blocking=True)
-        x = xyz_h.to(dev, non_blocking=True)
-        out = pipe.run(c, x, sizes, plan=prefetch.get(), descriptors=desc_d)   # fresh host RNG draws every step
-        rec = pipe.records(out, list(range(rank * P, rank * P + P)))
-        allrec = gather_records(rec, P * world)
-        rec_host.copy_(allrec[rank * P: rank * P + P] if world > 1 else allrec, non_blocking=True)
-        torch.cuda.synchronize()
-        return rec_host
+    def start_upload():
+        pl = prefetch.get()                                        # fresh host RNG draws (planned on a worker thread)
+        return uploader.start(coords=coords_h, xyz=xyz_h, fc0=pl['fc0'], fc1=pl['fc1'], src=pl['src'], tgt=pl['tgt']), pl
+
+    def run_e2e(n_steps):
+        ticket, pl = start_upload()
+        pending, last = None, None
+        for k in range(n_steps):
+            t = ticket.wait()
+            plan_k = dict(pl, fc0=t['fc0'], fc1=t['fc1'], src=t['src'], tgt=t['tgt'], fc_uniform=True)
+            ticket, pl = start_upload()                            # block k + 1 uploads while block k computes
+            out = pipe.run(t['coords'], t['xyz'], sizes, plan=plan_k, descriptors=desc_d)
+            ar = AsyncRecords(pipe.records(out, ids), P * world, host_out=rec_hosts[k & 1])
+            if pending is not None:
+                last = pending.result()                            # the host blocks on block k - 1's records only
+            pending = ar
+        last = pending.result()
+        return last
 
     for _ in range(W):
         allrec, out = step_resident()       # same tensor lifetimes as the timed loop (no allocator growth inside it)
@@ -281,15 +297,14 @@ def run_ours(args):
     value = P * world * K / (ms / 1e3)
 
     # ---- end-to-end timing through the public API with host inputs
-    prefetch = PlanPrefetcher(pipe, (sizes for _ in range(K + 2)))         # host RNG planning of block i+1 overlaps block i
-    for _ in range(2):
-        step_e2e()
+    prefetch = PlanPrefetcher(pipe, (sizes for _ in range(K + 8)))         # host RNG planning of block i+1 overlaps block i
+    run_e2e(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(K):
-        rec_e2e = step_e2e()
+    rec_e2e = run_e2e(K)
     barrier()
     e2e_s = time.perf_counter() - t0
+    h2d_bytes = uploader.bytes_last
     clocks = sampler.stop()
     prefetch.close()
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -386,8 +401,9 @@ def run_ours(args):
             'config': {'workload': WORKLOAD, 'pairs_per_gpu': P, 'global_pairs': P * world, 'voxels_per_step_per_gpu': int(coords_np.shape[0]),
                        'parallelism': f'pair-sharded x{world}', 'l2': 'per-step working set (>= 1 GB of level-1 features) exceeds the 126 MB L2; no explicit flush',
                        'value_mode': 'coordinates, points and index plans resident in HBM', 'conv_mode': enn.CONV_MODE, 'tile_order': bool(enn.TILE_ORDER)},
-            'e2e': {'value': e2e, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(coords_np.nbytes + xyz_np.nbytes + 2 * 8 * P * 8000 + 2 * 8 * P * 5000),
-                    'd2h_bytes_per_step': int(rec_host.numel() * 4), 'ms_per_step': 1e3 * e2e_s / K},
+            'e2e': {'value': e2e, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(h2d_bytes),
+                    'd2h_bytes_per_step': int(rec_hosts[0].numel() * 4), 'ms_per_step': 1e3 * e2e_s / K,
+                    'overlap': 'H2D of block i+1 on a copy stream, all-gather + D2H of block i on side streams (read by the host one block later)'},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'features_checked': features_checked,
             'gather_checked': gather_checked,
             'accuracy': {'rr_vs_gt': succ / P, 'rte_m_median': float(np.median(rtes)), 'rre_deg_median': float(np.nanmedian(rres))}}

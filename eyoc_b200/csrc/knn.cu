@@ -261,7 +261,9 @@ constexpr int TRT = 256;          // reference columns per accumulator tile (UMM
 constexpr int NS = 4;             // reference stages
 constexpr int PEND = 40;          // per-row list of columns awaiting exact re-scoring (a 32-column chunk can add 32)
 constexpr int ROWB = 128;         // bytes of a prepared row: 32 fp16 values | 2 fp16 norm columns | zero padding
-constexpr int NTH = 224;          // 4 epilogue warps, 2 producer warps, 1 MMA warp
+constexpr int NEW = 8;            // epilogue warps: two per TMEM lane quadrant, each draining half of a tile's columns (the
+                                  // drain - tcgen05.ld, wait, scan - is a latency chain per warp: two chains per scheduler)
+constexpr int NTH = (NEW + 3) * 32;   // epilogue warps, 2 producer warps, 1 MMA warp
 
 // fp32 rows -> prepared fp16 rows, |q| per query row, max |r| per batch, fallback flag per batch
 __global__ void knn_prep_kernel(const float* __restrict__ X, long long rows_per_batch, long long rows, int is_ref, int form,
@@ -342,18 +344,22 @@ knn_tc_kernel(const float* __restrict__ Q, const float* __restrict__ R, const ui
     if (tid == 0) {
         mbar_init(q_full, 64);
         for (int i = 0; i < NS; ++i) { mbar_init(r_full + 8 * i, 64); mbar_init(r_empty + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, NEW * 32); }
         mbar_init_fence();
     }
-    if (warp == 6) tmem_alloc(smem_u32(&tmem_base_s), 512);
+    if (warp == NEW + 2) tmem_alloc(smem_u32(&tmem_base_s), 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp < 4) {
-        // =========================================================== epilogue: thread = query row = TMEM lane
-        const int row = warp * 32 + lane;
+    if (warp < NEW) {
+        // =========================================================== epilogue: thread = query row = TMEM lane; the two warps
+        // of a lane quadrant take the lower / upper half of every tile's columns and keep independent candidates (each
+        // re-scores its own exactly; the 64-bit atomicMin merges them like it merges the reference splits)
+        const int quad = warp & 3, half = warp >> 2;
+        constexpr int CPW = (TRT / 32) / (NEW / 4);              // 32-column chunks per warp and tile
+        const int row = quad * 32 + lane;
         const int q = q0 + row;
         const bool live = q < nq;
         float qf[32];
@@ -369,7 +375,7 @@ knn_tc_kernel(const float* __restrict__ Q, const float* __restrict__ R, const ui
         float runmax = __int_as_float(0xff800000);
         float best = 0.f;              // raw accumulator of the exact winner so far
         int bestj = -1, cnt = 0;
-        int* const mypend = pend + row * PEND;
+        int* const mypend = pend + (half * TQ2 + row) * PEND;
         // exact re-scoring of the pending columns, in the order they were found (ascending): knn1_kernel's arithmetic
         auto flush = [&]() {
             for (int p = 0; p < cnt; ++p) {
@@ -406,9 +412,9 @@ knn_tc_kernel(const float* __restrict__ Q, const float* __restrict__ R, const ui
             tc_fence_after();
             const bool ragged = r0 + TRT > nr;                   // last tile: columns past nr must not raise the row maximum
 #pragma unroll 1
-            for (int ch = 0; ch < TRT / 32; ++ch) {
+            for (int ch = half * CPW; ch < (half + 1) * CPW; ++ch) {
                 uint32_t v[32];
-                const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * TRT + ch * 32);
+                const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * TRT + ch * 32);
                 tmem_ld16_nowait(ta, v);
                 tmem_ld16_nowait(ta + 16, v + 16);
                 tmem_ld_wait();
@@ -430,17 +436,17 @@ knn_tc_kernel(const float* __restrict__ Q, const float* __restrict__ R, const ui
                     for (int i = 0; i < 32; ++i)
                         if (__uint_as_float(v[i]) >= th) mypend[cnt++] = c0 + i;
                 }
-                if (ch == TRT / 32 - 1) {                        // accumulator drained: the MMA warp may reuse it
-                    tc_fence_before();
+                if (ch == (half + 1) * CPW - 1) {                // this warp's share is drained: the MMA warp may reuse it
+                    tc_fence_before();                           // once all NEW warps have arrived
                     mbar_arrive(acc_empty + 8 * ab);
                 }
-                if (cnt >= 8 || (ch == TRT / 32 - 1 && cnt > 0)) flush();
+                if (cnt >= 8 || (ch == (half + 1) * CPW - 1 && cnt > 0)) flush();
             }
         }
         if (live && bestj >= 0) atomicMin(keys + (size_t)b * nq + q, pack_key(value_of<FORM>(best), bestj));
-    } else if (warp < 6) {
+    } else if (warp < NEW + 2) {
         // =========================================================== producers: prepared rows -> SWIZZLE_128B operand tiles
-        const int w4 = warp - 4;
+        const int w4 = warp - NEW;
         const int c = lane & 7, rsub = lane >> 3;
         // the query tile: 128 rows, 64 per producer warp
 #pragma unroll
@@ -500,7 +506,7 @@ knn_tc_kernel(const float* __restrict__ Q, const float* __restrict__ R, const ui
         __syncwarp();
     }
     __syncthreads();
-    if (warp == 6) {
+    if (warp == NEW + 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
@@ -636,7 +642,7 @@ extern "C" int eyoc_knn1_tc(const float* q, const float* r, int batch, int64_t n
     nsplit = nsplit < 1 ? 1 : (nsplit > rtiles ? rtiles : nsplit);
     const int tiles_per_split = (rtiles + nsplit - 1) / nsplit;
     nsplit = (rtiles + tiles_per_split - 1) / tiles_per_split;
-    const size_t smem = (size_t)tck::TQ2 * tck::ROWB + (size_t)tck::NS * tck::TRT * tck::ROWB + (size_t)tck::TQ2 * tck::PEND * 4 + 1024;
+    const size_t smem = (size_t)tck::TQ2 * tck::ROWB + (size_t)tck::NS * tck::TRT * tck::ROWB + (size_t)(tck::NEW / 4) * tck::TQ2 * tck::PEND * 4 + 1024;
     dim3 grid(qtiles, nsplit, batch);
     if (form == 0) {
         EYOC_CUDA(cudaFuncSetAttribute(tck::knn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -98,10 +98,11 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm(
 constexpr int FO_COLS = 512;
 
 // exact classification of one entry (kept out of line: it runs for a handful of warp steps per million, and inlining it
-// into every unrolled copy of the inner loop made the kernel instruction-fetch bound)
-__device__ __noinline__ uint32_t first_order_exact(float ss, float tt, float d_thre, float d_half) {
+// into every unrolled copy of the inner loop made the kernel instruction-fetch bound).  Bit 31 of the three returned words
+// = hard / tight / near, the form the funnel-shift inserts of the inner loop take.
+__device__ __noinline__ uint3 first_order_exact(float ss, float tt, float d_thre, float d_half, float near_s0) {
     const float c = fabsf(__fsub_rn(__fsqrt_rn(ss), __fsqrt_rn(tt)));
-    return (uint32_t)(c < d_thre) | ((uint32_t)(c < d_half) << 1);
+    return make_uint3((c < d_thre) ? 0x80000000u : 0u, (c < d_half) ? 0x80000000u : 0u, !(ss >= near_s0) ? 0x80000000u : 0u);
 }
 
 __global__ void __launch_bounds__(128)
@@ -138,8 +139,11 @@ first_order_bits_kernel(const Pt* __restrict__ P, int n, int W, float d_thre, fl
         for (int cj = (A == B ? ri : 0); cj < 4; ++cj) {   // diagonal macro tile: blocks below its diagonal are mirror images
             uint32_t hb = 0, tb = 0, nb = 0;
             const int j0 = B * 128 + cj * 32;
+            // Columns are visited from 31 down to 0 and every result enters its word at bit 0 with ONE funnel shift
+            // (word = word << 1 | sign bit): for finite values `x < thr` is the sign of x - thr, which the margin test
+            // needs anyway.  Non-finite values make `unsure` true and go through the exact routine.
 #pragma unroll 4
-            for (int bp = 0; bp < 16; ++bp) {
+            for (int bp = 15; bp >= 0; --bp) {
                 const int c = cj * 32 + 2 * bp;
                 f32x2 dx = sub2(mx, *reinterpret_cast<const f32x2*>(col + c));
                 f32x2 dy = sub2(my, *reinterpret_cast<const f32x2*>(col + FO_COLS + c));
@@ -152,26 +156,36 @@ first_order_bits_kernel(const Pt* __restrict__ P, int n, int W, float d_thre, fl
                 float ss[2], tt[2];
                 unpack2(ss2, ss[0], ss[1]);
                 unpack2(tt2, tt[0], tt[1]);
-                uint32_t ht[2];
+                uint32_t wh[2], wt[2], wn[2];                  // bit 31 = the result
                 bool unsure = false;
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const float da = sqrt_approx(ss[e]), db = sqrt_approx(tt[e]);
                     const float ca = fabsf(da - db), mg = (da + db) * 9.5367431640625e-07f;      // 2^-20
-                    ht[e] = (uint32_t)(ca < d_thre) | ((uint32_t)(ca < d_half) << 1);
-                    unsure |= !(fabsf(ca - d_thre) > mg) || !(fabsf(ca - d_half) > mg);          // also true for NaN / Inf
+                    const float r1 = ca - d_thre, r2 = ca - d_half, r3 = ss[e] - near_s0;
+                    wh[e] = __float_as_uint(r1);
+                    wt[e] = __float_as_uint(r2);
+                    wn[e] = __float_as_uint(r3);
+                    unsure |= !(fabsf(r1) > mg) || !(fabsf(r2) > mg) || !(fabsf(r3) <= 3.0e38f);   // last: NaN / Inf sums
                 }
                 if (__any_sync(0xffffffffu, unsure)) {
-                    ht[0] = first_order_exact(ss[0], tt[0], d_thre, d_half);
-                    ht[1] = first_order_exact(ss[1], tt[1], d_thre, d_half);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const uint3 x = first_order_exact(ss[e], tt[e], d_thre, d_half, near_s0);
+                        wh[e] = x.x; wt[e] = x.y; wn[e] = x.z;
+                    }
                 }
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const uint32_t ok = (row_ok && j0 + 2 * bp + e < n) ? 1u : 0u;
-                    hb |= (ht[e] & ok) << (2 * bp + e);
-                    tb |= ((ht[e] >> 1) & ok) << (2 * bp + e);
-                    nb |= ((uint32_t)(!(ss[e] >= near_s0)) & ok) << (2 * bp + e);
+                for (int e = 1; e >= 0; --e) {
+                    hb = __funnelshift_l(wh[e], hb, 1);
+                    tb = __funnelshift_l(wt[e], tb, 1);
+                    nb = __funnelshift_l(wn[e], nb, 1);
                 }
+            }
+            {   // rows / columns beyond n: cleared per word, not per entry
+                const int valid = n - j0;                        // columns of this word that exist
+                const uint32_t cm = !row_ok || valid <= 0 ? 0u : (valid >= 32 ? 0xffffffffu : ((1u << valid) - 1u));
+                hb &= cm; tb &= cm; nb &= cm;
             }
             res[0][ri * 4 + cj][lane] = hb;
             res[1][ri * 4 + cj][lane] = tb;
@@ -679,11 +693,15 @@ __device__ __forceinline__ bool seed_consensus_body(const SeedArgs& a, const int
     }
     __syncthreads();
     // 4. local hard compatibility among the k1 (SC2_PCR.py:94-100; ((a-b)**2).sum(-1)**0.5 form)
-    for (int e = tid; e < k1 * k1; e += SC_NT) {
+    for (int e = tid; e < k1 * k1; e += SC_NT) {       // symmetric bit for bit ((a-b)^2 == (b-a)^2): upper triangle only
         const int p = e / k1, q = e % k1;
+        if (q < p) continue;
         const float ds = dist3_sum(ls[p][0], ls[p][1], ls[p][2], ls[q][0], ls[q][1], ls[q][2]);
         const float dt = dist3_sum(lt[p][0], lt[p][1], lt[p][2], lt[q][0], lt[q][1], lt[q][2]);
-        if (fabsf(__fsub_rn(ds, dt)) < a.d_thre) atomicOr(&lhard[p], 1u << q);
+        if (fabsf(__fsub_rn(ds, dt)) < a.d_thre) {
+            atomicOr(&lhard[p], 1u << q);
+            if (q != p) atomicOr(&lhard[q], 1u << p);
+        }
     }
     __syncthreads();
     if (tid < k1) {   // local_SC2[q] = sum_p hard[0][p] * hard[p][q]
@@ -707,12 +725,15 @@ __device__ __forceinline__ bool seed_consensus_body(const SeedArgs& a, const int
     // 5. soft measure on the k2 (SC2_PCR.py:117-131), diagonal zeroed
     for (int e = tid; e < k2 * k2; e += SC_NT) {
         const int p = e / k2, q = e % k2;
+        if (q < p) continue;
+        if (q == p) { M[p][p] = 0.f; continue; }
         const int fp = fine[p], fq = fine[q];
         const float ds = dist3_sum(ls[fp][0], ls[fp][1], ls[fp][2], ls[fq][0], ls[fq][1], ls[fq][2]);
         const float dt = dist3_sum(lt[fp][0], lt[fp][1], lt[fp][2], lt[fq][0], lt[fq][1], lt[fq][2]);
         const float c = fabsf(__fsub_rn(ds, dt));
         const float v = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fmul_rn(c, c), a.d_sq)), 0.f);
-        M[p][q] = (p == q) ? 0.f : v;
+        M[p][q] = v;
+        M[q][p] = v;
     }
     __syncthreads();
     // 6. power iteration on the k2 x k2 matrix by one warp, the lane's matrix row in registers; every iterate is kept
@@ -874,6 +895,7 @@ struct FitArgs {
     const int* local_notclose;
     int n, S, k2, num_iterations;
     float inlier_threshold;
+    float inlier_s0;       // sqrt_threshold(inlier_threshold)
     float* seed_weights;   // [batch, S, MAXK]
     float* seed_trans;     // [batch, S, 16]
     float* fitness;        // [batch, S]
@@ -948,7 +970,10 @@ seed_fitness_kernel(FitArgs a) {
         for (int k = 0; k < FS; ++k) {
             float x, y, z;
             apply_T(T[k], p.sx, p.sy, p.sz, x, y, z);
-            c[k] += dist3_fma(x, y, z, p.tx, p.ty, p.tz) < a.inlier_threshold;
+            // torch.norm(.) < thr  <=>  sum of squares < s0: sqrt_rn is monotonic and s0 (host: sqrt_threshold) is the
+            // smallest fp32 whose correctly rounded root reaches thr - the root itself is never formed
+            const float dx = __fsub_rn(x, p.tx), dy = __fsub_rn(y, p.ty), dz = __fsub_rn(z, p.tz);
+            c[k] += !(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))) >= a.inlier_s0);
         }
     }
 #pragma unroll
@@ -1324,7 +1349,7 @@ extern "C" int eyoc_sc2pcr(const float* src, const float* tgt, int batch, int n,
             seed_consensus_big_kernel<<<296, SC_NT, smem_big, stream>>>(sa);
             EYOC_LAUNCH_CHECK();
         }
-        FitArgs fa{P, topk2, local_v, local_notclose, n, S, L.k2, I, cfg->inlier_threshold, seed_weights, seed_trans,
+        FitArgs fa{P, topk2, local_v, local_notclose, n, S, L.k2, I, cfg->inlier_threshold, sqrt_threshold(cfg->inlier_threshold), seed_weights, seed_trans,
                    fitness ? fitness : scores /* scratch */, local_iters};
         if (!fitness) {
             EYOC_CHECK_ARG(S <= n, "unreachable");

@@ -201,6 +201,117 @@ class PlanPrefetcher:
             pass
 
 
+class BlockUploader:
+    """Host -> device copies of a block's inputs (coordinates, points, index plan) on a dedicated copy stream, one block
+    ahead of the compute stream: ``start(...)`` queues the copies of block i + 1 while block i computes, ``wait()`` makes the
+    compute stream wait for them (an event, no host synchronisation).  Host arrays are staged through pinned buffers owned
+    by the uploader (two sets, used alternately) so that every copy is truly asynchronous."""
+
+    class _Ticket:
+        def __init__(self, tensors, event, stream):
+            self.tensors, self.event, self.stream = tensors, event, stream
+
+        def wait(self):
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self.event)
+            for t in self.tensors.values():
+                if isinstance(t, torch.Tensor):
+                    t.record_stream(cur)                   # the caching allocator must not reuse them while `cur` reads
+            return self.tensors
+
+    def __init__(self, device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self._pinned = [{}, {}]
+        self._flip = 0
+        self.bytes_last = 0
+
+    def _stage(self, slot, key, a):
+        """numpy array / CPU tensor -> pinned CPU tensor (reused between blocks when the shape matches)."""
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+        if t.is_pinned():
+            return t
+        buf = slot.get(key)
+        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+            buf = slot[key] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+        buf.copy_(t)
+        return buf
+
+    def start(self, **host):
+        """host: name -> numpy array / CPU tensor (or a list of equally shaped arrays, stacked).  Returns a ticket."""
+        slot = self._pinned[self._flip]
+        self._flip ^= 1
+        out, nbytes = {}, 0
+        with torch.cuda.stream(self.stream):
+            for k, a in host.items():
+                if a is None:
+                    out[k] = None
+                    continue
+                if isinstance(a, (list, tuple)):
+                    a = np.stack(a)
+                src = self._stage(slot, k, a)
+                out[k] = src.to(self.device, non_blocking=True)
+                nbytes += src.numel() * src.element_size()
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.bytes_last = nbytes
+        return BlockUploader._Ticket(out, ev, self.stream)
+
+
+class AsyncRecords:
+    """The per-block result records on their way to the host: the all-gather runs asynchronously (NCCL's own stream) and
+    the device-to-host copy on a side stream, so the compute stream goes straight on to the next block; ``result()`` -
+    normally called one block later - blocks the HOST only, on the copy's event."""
+
+    def __init__(self, rec, num_pairs, group=None, host_out=None):
+        import torch.distributed as dist
+        self.num_pairs, self.group = num_pairs, group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.work = None
+        if self.world > 1:
+            self.m = -(-num_pairs // self.world)
+            pad = torch.zeros((self.m, rec.shape[1]), dtype=rec.dtype, device=rec.device)
+            pad[:rec.shape[0]] = rec
+            self.buf = torch.empty((self.world * self.m, rec.shape[1]), dtype=rec.dtype, device=rec.device)
+            self.pad = pad
+            self.work = dist.all_gather_into_tensor(self.buf, pad, group=group, async_op=True)
+        else:
+            self.buf = rec
+        self.side = _side_stream(rec.device)
+        self.host = host_out if host_out is not None else torch.empty(self.buf.shape, dtype=self.buf.dtype).pin_memory()
+        ready = torch.cuda.Event()
+        ready.record()                                        # rec (and, at world 1, buf) complete on the compute stream
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            if self.work is not None:
+                self.work.wait()                              # makes the SIDE stream wait for the collective
+            self.host[:self.buf.shape[0]].copy_(self.buf, non_blocking=True)
+            self.buf.record_stream(self.side)
+            self.done = torch.cuda.Event()
+            self.done.record(self.side)
+
+    def result(self):
+        """[num_pairs, RECORD_FLOATS] pinned CPU tensor (padding of uneven shards stripped)."""
+        self.done.synchronize()
+        if self.world == 1:
+            return self.host[:self.buf.shape[0]]
+        keep = []
+        for r in range(self.world):
+            lo, hi = shard_range(self.num_pairs, self.world, r)
+            keep.append(self.host[r * self.m: r * self.m + (hi - lo)])
+        return torch.cat(keep, 0)
+
+
+_SIDE = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
+
+
 def gather_records(rec, num_pairs, group=None):
     """The path's only collective: ONE all-gather of the per-pair records.  Every rank pads its block to
     ceil(num_pairs / world) rows (block sizes follow from ``shard_range``, so no size exchange is needed);
