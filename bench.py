@@ -29,6 +29,10 @@ KITTI_CFG = dict(inlier_threshold=0.6, num_node=8000, use_mutual=False, d_thre=0
 WORKLOAD = 'batch of synthetic KITTI pairs (~30k voxels/cloud, 0.3 m): ResUNetBN2C 32-D + find_corr NN + match_pair NN + SC2-PCR'
 
 
+def workload_name(model):
+    return WORKLOAD.replace('ResUNetBN2C', model)
+
+
 def _peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -149,11 +153,11 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------- our arm
-def build_model(device, seed=0):
+def build_model(device, seed=0, name='ResUNetBN2C'):
     import torch
     from eyoc_b200.model import load_model
     torch.manual_seed(seed)
-    model = load_model('ResUNetBN2C')(1, 32, bn_momentum=0.05, normalize_feature=True, conv1_kernel_size=5, D=3)
+    model = load_model(name)(1, 32, bn_momentum=0.05, normalize_feature=True, conv1_kernel_size=5, D=3)
     g = torch.Generator().manual_seed(seed + 1)
     with torch.no_grad():      # non-trivial BatchNorm statistics (random-init weights; no checkpoint is reachable)
         for m in model.modules():
@@ -216,7 +220,7 @@ def run_ours(args):
     coords_h, xyz_h = torch.from_numpy(coords_np).pin_memory(), torch.from_numpy(xyz_np).pin_memory()
     coords_d, xyz_d = coords_h.to(dev), xyz_h.to(dev)
     desc_d = torch.from_numpy(desc_np).to(dev) if args.descriptors == 'planted' else None
-    model = build_model(dev)
+    model = build_model(dev, name=args.model)
     pipe = RegistrationPipeline(model, Matcher(**KITTI_CFG))
     np.random.seed(1000 + rank)
     plan_d = plan_to_device(pipe.plan(sizes), dev)
@@ -248,10 +252,12 @@ def run_ours(args):
         ticket, pl = start_upload()
         pending, last = None, None
         for k in range(n_steps):
+            cur_ticket = ticket
             t = ticket.wait()
             plan_k = dict(pl, fc0=t['fc0'], fc1=t['fc1'], src=t['src'], tgt=t['tgt'], fc_uniform=True)
             ticket, pl = start_upload()                            # block k + 1 uploads while block k computes
             out = pipe.run(t['coords'], t['xyz'], sizes, plan=plan_k, descriptors=desc_d)
+            cur_ticket.release()                                   # its buffers may be refilled two blocks from now
             ar = AsyncRecords(pipe.records(out, ids), P * world, host_out=rec_hosts[k & 1])
             if pending is not None:
                 last = pending.result()                            # the host blocks on block k - 1's records only
@@ -398,7 +404,7 @@ def run_ours(args):
             'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic KITTI-shaped LiDAR pairs (ray-cast generator, seeded); random-init weights'
                     + ('; estimator fed planted descriptors (the forward pass still runs and is timed)' if desc_d is not None else ''),
-            'config': {'workload': WORKLOAD, 'pairs_per_gpu': P, 'global_pairs': P * world, 'voxels_per_step_per_gpu': int(coords_np.shape[0]),
+            'config': {'workload': workload_name(args.model), 'pairs_per_gpu': P, 'global_pairs': P * world, 'voxels_per_step_per_gpu': int(coords_np.shape[0]),
                        'parallelism': f'pair-sharded x{world}', 'l2': 'per-step working set (>= 1 GB of level-1 features) exceeds the 126 MB L2; no explicit flush',
                        'value_mode': 'coordinates, points and index plans resident in HBM', 'conv_mode': enn.CONV_MODE, 'tile_order': bool(enn.TILE_ORDER)},
             'e2e': {'value': e2e, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(h2d_bytes),
@@ -407,7 +413,7 @@ def run_ours(args):
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'features_checked': features_checked,
             'gather_checked': gather_checked,
             'accuracy': {'rr_vs_gt': succ / P, 'rte_m_median': float(np.median(rtes)), 'rre_deg_median': float(np.nanmedian(rres))}}
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.model == 'ResUNetBN2C':
         pps, dt, n, cores, per = run_cpu(list(range(args.cpu_pairs + 1)), warmup=1)
         line['cpu_baseline'] = {'value': pps, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port', 'dense_weight': False,
                                 'sample': f'median of {n} pairs of the same generator after 1 warm-up pair ({dt:.1f} s in all, per pair '
@@ -432,6 +438,8 @@ def main():
     ap.add_argument('--pairs-per-gpu', type=int, default=64)
     ap.add_argument('--descriptors', default='planted', choices=['planted', 'network'])
     ap.add_argument('--conv-mode', default=None, choices=['fp32', 'tf32x3', 'f16x3'])
+    ap.add_argument('--model', default='ResUNetBN2C', help='feature extractor (model/resunet.py): ResUNetBN2C (the reference default, '
+                    'config.py:82), ResUNetFatBN (scripts/test_waymo.sh:13), ResUNetExpBN2C, ...')
     ap.add_argument('--cpu-pairs', type=int, default=5)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-check-gather', action='store_true',

@@ -431,7 +431,7 @@ knn_tc_kernel(const float* __restrict__ Q, const float* __restrict__ R, const ui
                 // form 1: a product > 1 makes sqrt(2 - 2 s + 1e-6) NaN, and torch.argmin returns the FIRST NaN column
                 // whatever its s: every column whose score can exceed 1 is queued, not only those near the row maximum
                 const float th = (FORM == 1 ? fminf(runmax, 1.0f) : runmax) - tau;
-                if (live && cm >= th) {
+                if (live && cm >= th && cm > __int_as_float(0xff800000)) {      // (a chunk wholly past nr holds only -inf)
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
                         if (__uint_as_float(v[i]) >= th) mypend[cnt++] = c0 + i;

@@ -688,6 +688,27 @@ __global__ void xh_unpack_kernel(const uint8_t* __restrict__ xh, long long n8, i
     *reinterpret_cast<float4*>(x + r * c + col + 4) = make_float4(y[4], y[5], y[6], y[7]);
 }
 
+// y = x * scale + shift per channel on split-half rows (a stand-alone eval BatchNorm, model/resunet.py:404-408 of the
+// Expanded variants); one thread per 8 channels
+__global__ void xh_affine_kernel(const uint8_t* __restrict__ in, long long n8, int c, const float* __restrict__ scale,
+                                 const float* __restrict__ shift, uint8_t* __restrict__ out, int* __restrict__ range_status) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    const int c8n = c >> 3;
+    const long long r = i / c8n;
+    const int col = (int)(i - r * c8n) * 8;
+    float y[8];
+    xh_load8(in + (size_t)r * c * 4, col, y);
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        y[j] = __fmaf_rn(y[j], __ldg(scale + col + j), __ldg(shift + col + j));
+        bad |= !(fabsf(y[j]) < 65504.f);
+    }
+    if (bad && range_status) atomicOr(range_status, 1);
+    xh_store8(out + (size_t)r * c * 4, col, y);
+}
+
 // masks[t] = OR over the 256 columns of tile t of the bit mask "offset k has a neighbour"
 __global__ void tile_masks_kernel(const int* __restrict__ nbr, int K, int n_out, uint32_t* __restrict__ masks) {
     __shared__ uint32_t m_s;
@@ -786,6 +807,16 @@ extern "C" int eyoc_xh_pack(const float* x, int64_t n, int c, void* xh, int32_t*
     if (n == 0) return EYOC_OK;
     const long long n8 = (long long)n * (c / 8);
     xh_pack_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>(x, n8, c, (uint8_t*)xh, range_status);
+    EYOC_LAUNCH_CHECK();
+    return EYOC_OK;
+}
+
+extern "C" int eyoc_xh_affine(const void* in, int64_t n, int c, const float* scale, const float* shift, void* out,
+                              int32_t* range_status, cudaStream_t stream) {
+    EYOC_CHECK_ARG(in && out && scale && shift && n >= 0 && c >= 32 && c % 32 == 0, "eyoc_xh_affine: bad argument (c must be a multiple of 32)");
+    if (n == 0) return EYOC_OK;
+    const long long n8 = (long long)n * (c / 8);
+    xh_affine_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>((const uint8_t*)in, n8, c, scale, shift, (uint8_t*)out, range_status);
     EYOC_LAUNCH_CHECK();
     return EYOC_OK;
 }

@@ -12,7 +12,7 @@ from .. import nn as enn
 from ..nn import MinkowskiConvolution, MinkowskiConvolutionTranspose, conv_bn_act
 from ..sparse import SparseTensor
 from .common import get_norm
-from .residual_block import get_block
+from .residual_block import get_block  # noqa: F401  (ResUNetExpanded builds its second blocks with it)
 
 
 class ResUNet2(nn.Module):
@@ -140,3 +140,44 @@ class ResUNetFatBN(ResUNet2):
     NORM_TYPE = 'BN'
     CHANNELS = [None, 32, 64, 128, 256]
     TR_CHANNELS = [None, 128, 128, 128, 256]
+
+
+class ResUNetExpanded(ResUNet2):
+    """model/resunet.py:254-486: every level runs two residual blocks with a stand-alone norm in between
+    (norm -> block -> ReLU -> norm_2 -> block_2 -> ReLU).  Same sub-module names / state-dict keys as the reference."""
+    NORM_TYPE = None
+    BLOCK_NORM_TYPE = 'BN'
+    CHANNELS = [None, 32, 64, 128, 256]
+    TR_CHANNELS = [None, 32, 64, 64, 128]
+
+    def __init__(self, in_channels=3, out_channels=32, bn_momentum=0.1, normalize_feature=None, conv1_kernel_size=None, D=3):
+        super().__init__(in_channels, out_channels, bn_momentum, normalize_feature, conv1_kernel_size, D)
+        C, T = self.CHANNELS, self.TR_CHANNELS
+        for name, c in (('1', C[1]), ('2', C[2]), ('3', C[3]), ('4', C[4]), ('4_tr', T[4]), ('3_tr', T[3]), ('2_tr', T[2])):
+            setattr(self, f'norm{name}_2', get_norm(self.NORM_TYPE, c, bn_momentum=bn_momentum, D=D))
+            setattr(self, f'block{name}_2', get_block(self.BLOCK_NORM_TYPE, c, c, bn_momentum=bn_momentum, D=D))
+
+    def _level(self, x, name):
+        """block -> (ReLU: idempotent) -> norm_2 -> block_2 (-> ReLU: idempotent), resunet.py:398-408."""
+        x = getattr(self, f'block{name}')(x)
+        return getattr(self, f'block{name}_2')(getattr(self, f'norm{name}_2')(x))
+
+    def _forward(self, x):
+        """model/resunet.py:396-486."""
+        with torch.no_grad():
+            out_s1 = self._level(conv_bn_act(x, self.conv1, self.norm1), '1')
+            out_s2 = self._level(conv_bn_act(out_s1, self.conv2, self.norm2), '2')
+            out_s4 = self._level(conv_bn_act(out_s2, self.conv3, self.norm3), '3')
+            out_s8 = self._level(conv_bn_act(out_s4, self.conv4, self.norm4), '4')
+            out_s4_tr = self._level(conv_bn_act(out_s8, self.conv4_tr, self.norm4_tr), '4_tr')
+            out_s2_tr = self._level(conv_bn_act(out_s4_tr, self.conv3_tr, self.norm3_tr, skip=out_s4), '3_tr')
+            out_s1_tr = self._level(conv_bn_act(out_s2_tr, self.conv2_tr, self.norm2_tr, skip=out_s2), '2_tr')
+            out = conv_bn_act(out_s1_tr, self.conv1_tr, relu=True, skip=out_s1)
+            return conv_bn_act(out, self.final, l2norm=bool(self.normalize_feature))
+
+
+class ResUNetExpBN2C(ResUNetExpanded):
+    """model/resunet.py:489-492."""
+    NORM_TYPE = 'BN'
+    CHANNELS = [None, 32, 64, 128, 256]
+    TR_CHANNELS = [None, 64, 64, 64, 128]

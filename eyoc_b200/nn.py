@@ -102,11 +102,18 @@ class MinkowskiBatchNorm(nn.Module):
         return cache[1], cache[2]
 
     def forward(self, x):
-        """Stand-alone eval BatchNorm (module-level compatibility only: the fused forward folds it into the
-        producing convolution's epilogue and never calls this)."""
+        """Stand-alone eval BatchNorm (model/resunet.py:404-408, the Expanded variants; everywhere else the fused forward
+        folds the norm into the producing convolution's epilogue).  Split-half features stay split-half (eyoc_xh_affine)."""
         scale, shift = self.folded()
-        return SparseTensor(x.F * scale + shift, coordinate_map_key=x.coordinate_map_key,
-                            coordinate_manager=x.coordinate_manager)
+        mgr = x.coordinate_manager
+        if x._Fh is not None and x._F is None:
+            out = torch.empty_like(x._Fh)
+            n, c = x._Fh.shape[0], x._Fh.shape[1] // 2
+            with torch.cuda.device(out.device):
+                _C.check(_C.lib().eyoc_xh_affine(_C.ptr(x._Fh), _C.c_int64(n), _C.c_int(c), _C.ptr(scale), _C.ptr(shift), _C.ptr(out),
+                                                 _C.ptr(mgr.range_status), _C.stream()))
+            return SparseTensor(features_xh=out, coordinate_map_key=x.coordinate_map_key, coordinate_manager=mgr)
+        return SparseTensor(x.F * scale + shift, coordinate_map_key=x.coordinate_map_key, coordinate_manager=mgr)
 
 
 # Data path of the convolutions that qualify (C_in multiple of 32, C_out in {32,64,128,256}, K <= 27):

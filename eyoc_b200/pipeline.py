@@ -203,59 +203,72 @@ class PlanPrefetcher:
 
 class BlockUploader:
     """Host -> device copies of a block's inputs (coordinates, points, index plan) on a dedicated copy stream, one block
-    ahead of the compute stream: ``start(...)`` queues the copies of block i + 1 while block i computes, ``wait()`` makes the
-    compute stream wait for them (an event, no host synchronisation).  Host arrays are staged through pinned buffers owned
-    by the uploader (two sets, used alternately) so that every copy is truly asynchronous."""
+    ahead of the compute stream: ``start(...)`` queues the copies of block i + 1 while block i computes, ``ticket.wait()``
+    makes the compute stream wait for them (an event, no host synchronisation), ``ticket.release()`` - called once the
+    block's kernels are queued - lets the uploader reuse the buffers two blocks later.  Pinned staging buffers and device
+    buffers are owned by the uploader (two sets, used alternately), so the steady state allocates nothing."""
 
     class _Ticket:
-        def __init__(self, tensors, event, stream):
-            self.tensors, self.event, self.stream = tensors, event, stream
+        def __init__(self, owner, slot, tensors, event):
+            self.owner, self.slot, self.tensors, self.event = owner, slot, tensors, event
 
         def wait(self):
-            cur = torch.cuda.current_stream()
-            cur.wait_event(self.event)
-            for t in self.tensors.values():
-                if isinstance(t, torch.Tensor):
-                    t.record_stream(cur)                   # the caching allocator must not reuse them while `cur` reads
+            torch.cuda.current_stream().wait_event(self.event)
             return self.tensors
+
+        def release(self):
+            ev = torch.cuda.Event()
+            ev.record()                                     # on the compute stream: everything that reads the buffers is queued
+            self.owner._free[self.slot] = ev
 
     def __init__(self, device):
         self.device = device
         self.stream = torch.cuda.Stream(device=device)
         self._pinned = [{}, {}]
+        self._dev = [{}, {}]
+        self._free = [None, None]       # compute-stream events: the device buffers of a set may be overwritten
+        self._copied = [None, None]     # copy-stream events: the pinned staging buffers of a set may be overwritten
         self._flip = 0
         self.bytes_last = 0
 
-    def _stage(self, slot, key, a):
-        """numpy array / CPU tensor -> pinned CPU tensor (reused between blocks when the shape matches)."""
-        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
-        if t.is_pinned():
-            return t
-        buf = slot.get(key)
-        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
-            buf = slot[key] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
-        buf.copy_(t)
+    @staticmethod
+    def _buf(pool, key, like, make):
+        buf = pool.get(key)
+        if buf is None or buf.shape != like.shape or buf.dtype != like.dtype:
+            buf = pool[key] = make()
         return buf
 
     def start(self, **host):
         """host: name -> numpy array / CPU tensor (or a list of equally shaped arrays, stacked).  Returns a ticket."""
-        slot = self._pinned[self._flip]
+        slot = self._flip
         self._flip ^= 1
+        pinned, devp = self._pinned[slot], self._dev[slot]
         out, nbytes = {}, 0
         with torch.cuda.stream(self.stream):
+            if self._free[slot] is not None:
+                self.stream.wait_event(self._free[slot])    # the block that last used this set has been consumed
             for k, a in host.items():
                 if a is None:
                     out[k] = None
                     continue
                 if isinstance(a, (list, tuple)):
                     a = np.stack(a)
-                src = self._stage(slot, k, a)
-                out[k] = src.to(self.device, non_blocking=True)
-                nbytes += src.numel() * src.element_size()
+                t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+                if not t.is_pinned():
+                    stage = self._buf(pinned, k, t, lambda: torch.empty(t.shape, dtype=t.dtype).pin_memory())
+                    if self._copied[slot] is not None:
+                        self._copied[slot].synchronize()    # this set's previous H2D (two blocks ago) has long completed
+                    stage.copy_(t)
+                    t = stage
+                dst = self._buf(devp, k, t, lambda: torch.empty(t.shape, dtype=t.dtype, device=self.device))
+                dst.copy_(t, non_blocking=True)
+                out[k] = dst
+                nbytes += t.numel() * t.element_size()
             ev = torch.cuda.Event()
             ev.record(self.stream)
+        self._copied[slot] = ev
         self.bytes_last = nbytes
-        return BlockUploader._Ticket(out, ev, self.stream)
+        return BlockUploader._Ticket(self, slot, out, ev)
 
 
 class AsyncRecords:

@@ -220,6 +220,10 @@ size_t eyoc_convh_weight_image_halves(int K, int cin, int cout);
 int eyoc_convh_split_weights(const float* weight, int K, int cin, int cout, float wscale, void* wt_img, eyoc_stream_t stream);
 int eyoc_xh_pack(const float* x, int64_t n, int c, void* xh, int32_t* range_status, eyoc_stream_t stream);
 int eyoc_xh_unpack(const void* xh, int64_t n, int c, float* x, eyoc_stream_t stream);
+/* out = in * scale + shift per channel, split-half in and out: a stand-alone eval ME.MinkowskiBatchNorm between two blocks
+ * (model/resunet.py:404-408, the ResUNetExpanded variants).  In-place (out == in) is allowed. */
+int eyoc_xh_affine(const void* in, int64_t n, int c, const float* scale, const float* shift, void* out, int32_t* range_status,
+                   eyoc_stream_t stream);
 int eyoc_tile_masks(const int32_t* nbr_tiled, int K, int64_t n_out, uint32_t* masks, eyoc_stream_t stream);
 int eyoc_sparse_conv_h_supported(int c0, int c1, int cout, int K, int l2norm);
 int eyoc_sparse_conv_h(const void* in0, int c0, const void* in1, int c1, const int32_t* nbr, int K, int64_t n_out,

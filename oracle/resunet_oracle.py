@@ -212,3 +212,56 @@ def dense_conv_reference(coords_in, x, coords_out, W, ksize, ts_in, stride, tran
         y = F.conv_transpose3d(g, Wd.permute(1, 0, 2, 3, 4).contiguous(), stride=stride, padding=r)
         oi = co - lo * stride
     return y[0, :, oi[:, 0], oi[:, 1], oi[:, 2]].t()
+
+
+# ------------------------------------------------------------- ResUNetExpanded (model/resunet.py:254-492)
+def make_state_dict_expanded(in_channels=1, out_channels=32, conv1_kernel_size=5, seed=0, channels=None, tr_channels=None,
+                             dtype=torch.float32):
+    """State dict of ResUNetExpBN2C: ResUNetBN2C's keys plus ``norm<L>_2`` / ``block<L>_2`` for every level."""
+    C = channels or CHANNELS
+    T = tr_channels or TR_CHANNELS
+    sd = make_state_dict(in_channels, out_channels, conv1_kernel_size, seed=seed, dtype=dtype)
+    g = torch.Generator().manual_seed(seed + 1000)
+    for name, c in (('1', C[1]), ('2', C[2]), ('3', C[3]), ('4', C[4]), ('4_tr', T[4]), ('3_tr', T[3]), ('2_tr', T[2])):
+        pre = f'norm{name}_2'
+        sd[pre + '.bn.weight'] = (torch.rand(c, generator=g) + 0.5).to(dtype)
+        sd[pre + '.bn.bias'] = (torch.randn(c, generator=g) * 0.1).to(dtype)
+        sd[pre + '.bn.running_mean'] = (torch.randn(c, generator=g) * 0.1).to(dtype)
+        sd[pre + '.bn.running_var'] = (torch.rand(c, generator=g) + 0.5).to(dtype)
+        sd[pre + '.bn.num_batches_tracked'] = torch.tensor(0, dtype=torch.long)
+        for cv in ('conv1', 'conv2'):
+            bound = 1.0 / np.sqrt(c * 27)
+            sd[f'block{name}_2.{cv}.kernel'] = ((torch.rand((27, c, c), generator=g) * 2 - 1) * bound).to(dtype)
+        for nm in ('norm1', 'norm2'):
+            p2 = f'block{name}_2.{nm}'
+            sd[p2 + '.bn.weight'] = (torch.rand(c, generator=g) + 0.5).to(dtype)
+            sd[p2 + '.bn.bias'] = (torch.randn(c, generator=g) * 0.1).to(dtype)
+            sd[p2 + '.bn.running_mean'] = (torch.randn(c, generator=g) * 0.1).to(dtype)
+            sd[p2 + '.bn.running_var'] = (torch.rand(c, generator=g) + 0.5).to(dtype)
+            sd[p2 + '.bn.num_batches_tracked'] = torch.tensor(0, dtype=torch.long)
+    return sd
+
+
+def resunet_expanded_forward(coords, feats, sd, normalize_feature=True, conv1_kernel_size=5, maps=None):
+    """model/resunet.py:396-486 (ResUNetExpanded.forward)."""
+    maps = maps or build_maps(coords, conv1_kernel_size)
+    s1, dn, up = maps['s1'], maps['down'], maps['up']
+
+    def level(x, name, nbr):
+        x = F.relu(_block(x, sd, f'block{name}', nbr))
+        x = _bn(x, sd, f'norm{name}_2')
+        return F.relu(_block(x, sd, f'block{name}_2', nbr))
+
+    x = torch.as_tensor(feats)
+    o1 = level(_bn(sparse_conv(x, sd['conv1.kernel'], maps['k5']), sd, 'norm1'), '1', s1[0])
+    o2 = level(_bn(sparse_conv(o1, sd['conv2.kernel'], dn[0]), sd, 'norm2'), '2', s1[1])
+    o4 = level(_bn(sparse_conv(o2, sd['conv3.kernel'], dn[1]), sd, 'norm3'), '3', s1[2])
+    o8 = level(_bn(sparse_conv(o4, sd['conv4.kernel'], dn[2]), sd, 'norm4'), '4', s1[3])
+    o4t = level(_bn(sparse_conv(o8, sd['conv4_tr.kernel'], up[2]), sd, 'norm4_tr'), '4_tr', s1[2])
+    o2t = level(_bn(sparse_conv(torch.cat([o4t, o4], 1), sd['conv3_tr.kernel'], up[1]), sd, 'norm3_tr'), '3_tr', s1[1])
+    o1t = level(_bn(sparse_conv(torch.cat([o2t, o2], 1), sd['conv2_tr.kernel'], up[0]), sd, 'norm2_tr'), '2_tr', s1[0])
+    out = F.relu(torch.cat([o1t, o1], 1) @ sd['conv1_tr.kernel'])
+    out = out @ sd['final.kernel'] + sd['final.bias']
+    if normalize_feature:
+        out = out / torch.norm(out, p=2, dim=1, keepdim=True)
+    return out

@@ -229,3 +229,21 @@ def test_range_guard_falls_back_to_fp32_activations():
         model(x2)
     assert not w2, [str(m.message) for m in w2]
     assert int(x2.coordinate_manager.range_status.item()) == 0
+
+
+def test_forward_expanded_variant_vs_oracle():
+    """ResUNetExpBN2C (model/resunet.py:254-492): two residual blocks per level with a stand-alone eval BatchNorm between
+    them (eyoc_xh_affine on split-half rows) - same state-dict keys as the reference, features within 1e-5 of the oracle."""
+    from eyoc_b200.model import load_model
+    from eyoc_b200.sparse import SparseTensor
+    from oracle import resunet_oracle as RO
+    from tests.test_resunet_gpu import _cloud
+    coords = _cloud(2500, 12, batch=2)
+    feats = torch.ones((len(coords), 1), dtype=torch.float32)
+    sd = RO.make_state_dict_expanded(1, 32, 5, seed=6)
+    model = load_model('ResUNetExpBN2C')(1, 32, bn_momentum=0.05, normalize_feature=True, conv1_kernel_size=5, D=3)
+    model.load_state_dict(sd)                                    # strict: every reference key present, none extra
+    model = model.cuda().eval()
+    want = RO.resunet_expanded_forward(coords, feats, sd, True, 5)
+    got = model(SparseTensor(feats.cuda(), coordinates=torch.from_numpy(coords).cuda())).F.cpu()
+    assert float((got - want).abs().max()) <= 1e-5, float((got - want).abs().max())
