@@ -209,6 +209,8 @@ def run_ours(args):
         enn.CONV_MODE = args.conv_mode
     if args.no_tile_order:
         enn.TILE_ORDER = False
+    if args.wide_issuers:
+        lib.eyoc_debug_convh_wide_issuers(_C.c_int(args.wide_issuers))
     if args.tile_group_mb:
         from eyoc_b200 import sparse as esp
         esp.TILE_GROUP_BYTES = args.tile_group_mb * 1e6
@@ -248,21 +250,33 @@ def run_ours(args):
         pl = prefetch.get()                                        # fresh host RNG draws (planned on a worker thread)
         return uploader.start(coords=coords_h, xyz=xyz_h, fc0=pl['fc0'], fc1=pl['fc1'], src=pl['src'], tgt=pl['tgt']), pl
 
+    e2e_phase = {}
+
     def run_e2e(n_steps):
         ticket, pl = start_upload()
         pending, last = None, None
+        acc = [0.0] * 5
         for k in range(n_steps):
+            t0_ = time.perf_counter()
             cur_ticket = ticket
             t = ticket.wait()
             plan_k = dict(pl, fc0=t['fc0'], fc1=t['fc1'], src=t['src'], tgt=t['tgt'], fc_uniform=True)
             ticket, pl = start_upload()                            # block k + 1 uploads while block k computes
+            t1_ = time.perf_counter()
             out = pipe.run(t['coords'], t['xyz'], sizes, plan=plan_k, descriptors=desc_d)
             cur_ticket.release()                                   # its buffers may be refilled two blocks from now
+            t2_ = time.perf_counter()
             ar = AsyncRecords(pipe.records(out, ids), P * world, host_out=rec_hosts[k & 1])
+            t3_ = time.perf_counter()
             if pending is not None:
                 last = pending.result()                            # the host blocks on block k - 1's records only
             pending = ar
+            t4_ = time.perf_counter()
+            for i_, d_ in enumerate((t1_ - t0_, t2_ - t1_, t3_ - t2_, t4_ - t3_)):
+                acc[i_] += d_
         last = pending.result()
+        e2e_phase.update(host_ms_per_step={'upload_start': 1e3 * acc[0] / n_steps, 'pipe_run_launch': 1e3 * acc[1] / n_steps,
+                                           'records_async': 1e3 * acc[2] / n_steps, 'wait_prev_records': 1e3 * acc[3] / n_steps})
         return last
 
     for _ in range(W):
@@ -409,6 +423,7 @@ def run_ours(args):
                        'value_mode': 'coordinates, points and index plans resident in HBM', 'conv_mode': enn.CONV_MODE, 'tile_order': bool(enn.TILE_ORDER)},
             'e2e': {'value': e2e, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(h2d_bytes),
                     'd2h_bytes_per_step': int(rec_hosts[0].numel() * 4), 'ms_per_step': 1e3 * e2e_s / K,
+                    'host_phases': e2e_phase.get('host_ms_per_step'),
                     'overlap': 'H2D of block i+1 on a copy stream, all-gather + D2H of block i on side streams (read by the host one block later)'},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'features_checked': features_checked,
             'gather_checked': gather_checked,
@@ -446,6 +461,7 @@ def main():
                     help='skip the world > 1 self-check (rank 0 recomputes every rank\'s block and compares the gathered table byte for byte)')
     ap.add_argument('--conv-breakdown', action='store_true')
     ap.add_argument('--no-tile-order', action='store_true')
+    ap.add_argument('--wide-issuers', type=int, default=0, help='tuning: MMA-issuing threads of the 128-channel conv instantiation')
     ap.add_argument('--tile-group-mb', type=float, default=None, help='L2 budget of one cloud group of the tile order (sparse.TILE_GROUP_BYTES)')
     args = ap.parse_args()
     if args.gpus > 1 and 'RANK' not in os.environ:        # convenience: self-launch one rank per GPU

@@ -125,10 +125,10 @@ __device__ __forceinline__ void bar_sync_producers() { asm volatile("bar.sync 1,
 // WIDE = false: C_out <= 64, W_hi / W_lo stacked along M (64 lanes each), 4 MMAs per item.  WIDE = true: 128 output
 // channels per CTA (blockIdx.y selects the half when C_out = 256), W_hi and W_lo are separate 128-row operands, 6 MMAs.
 // Thread map: 16 producer warps (also the epilogue), one weight-loader warp, two MMA-issuer warps (one elected thread each).
-template <bool WIDE, int NSW, int NXS, bool DBG>
+template <bool WIDE, int NSW, int NXS, bool DBG, bool WIDE2 = false>
 __global__ void __launch_bounds__(NPT + 96, 1)
 sparse_conv_h_kernel(HArgs a) {
-    constexpr bool PER_TILE = !WIDE;                          // one MMA-issuing thread per tile (see "MMA issuers")
+    constexpr bool PER_TILE = !WIDE || WIDE2;                          // one MMA-issuing thread per tile (see "MMA issuers")
     constexpr int NMMA = PER_TILE ? NTILE : 1;                // MMA-issuing threads
     static_assert(RB * NXS > NXS + NG + 2 * NSW + 2, "barrier rotation too short for the ring depths");
     constexpr int W_BYTES = (WIDE ? 256 : 128) * 128;         // slab: 128 (hi 64 | lo 64) or 256 (hi 128 | lo 128) rows of 128 B
@@ -733,10 +733,10 @@ __global__ void tile_masks_kernel(const int* __restrict__ nbr, int K, int n_out,
 int h_ablate = 0;      // host copy of g_ablate: non-zero selects the instrumented instantiation
 int h_grid_cap = 0;    // tests: cap on gridDim.x, so that small inputs walk many tile pairs per persistent CTA
 
-template <bool WIDE, int NSW, int NXS, bool DBG>
+template <bool WIDE, int NSW, int NXS, bool DBG, bool WIDE2 = false>
 int launch_h2(const HArgs& a, cudaStream_t stream) {
     const size_t smem = (size_t)NXS * XS_BYTES + (size_t)NSW * (WIDE ? 256 : 128) * 128;
-    EYOC_CUDA(cudaFuncSetAttribute(sparse_conv_h_kernel<WIDE, NSW, NXS, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EYOC_CUDA(cudaFuncSetAttribute(sparse_conv_h_kernel<WIDE, NSW, NXS, DBG, WIDE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = (a.n_out + TR - 1) / TR;
     static std::atomic<int> sms_of[64];                     // SM count per device ordinal (0 = not queried yet)
     int dev = 0;
@@ -753,12 +753,14 @@ int launch_h2(const HArgs& a, cudaStream_t stream) {
     dim3 grid(gx, parts);
     // the launch's own hand-out counters, cleared in stream order: nothing is shared between launches in flight
     EYOC_CUDA(cudaMemsetAsync(a.counters, 0, 2 * sizeof(unsigned int), stream));
-    sparse_conv_h_kernel<WIDE, NSW, NXS, DBG><<<grid, NPT + 96, smem, stream>>>(a);
+    sparse_conv_h_kernel<WIDE, NSW, NXS, DBG, WIDE2><<<grid, NPT + 96, smem, stream>>>(a);
     EYOC_LAUNCH_CHECK();
     return EYOC_OK;
 }
+int h_wide_issuers = 1;   // MMA-issuing threads of the 128-channel kernel: 1 (one thread, probing ahead) or 2 (one per tile)
 template <bool WIDE, int NSW, int NXS>
 int launch_h(const HArgs& a, cudaStream_t stream) {
+    if (WIDE && h_wide_issuers == 2 && !h_ablate) return launch_h2<WIDE, NSW, NXS, false, WIDE>(a, stream);
     return h_ablate ? launch_h2<WIDE, NSW, NXS, true>(a, stream) : launch_h2<WIDE, NSW, NXS, false>(a, stream);
 }
 
@@ -767,6 +769,11 @@ int launch_h(const HArgs& a, cudaStream_t stream) {
 extern "C" int eyoc_debug_convh_ablate(int flags) {
     h_ablate = flags;
     EYOC_CUDA(cudaMemcpyToSymbol(g_ablate, &flags, sizeof(int)));
+    return EYOC_OK;
+}
+
+extern "C" int eyoc_debug_convh_wide_issuers(int n) {
+    h_wide_issuers = n == 2 ? 2 : 1;
     return EYOC_OK;
 }
 

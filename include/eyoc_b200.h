@@ -233,6 +233,8 @@ int eyoc_sparse_conv_h(const void* in0, int c0, const void* in1, int c1, const i
                        eyoc_stream_t stream);
 /* Test aid: cap gridDim.x of the persistent grid (0 = one CTA per SM), so that small inputs walk many tile pairs per CTA. */
 int eyoc_debug_convh_grid_cap(int max_ctas);
+/* Tuning aid: 1 = one MMA-issuing thread in the 128-channel instantiation (default), 2 = one per accumulator tile. */
+int eyoc_debug_convh_wide_issuers(int n);
 /* Measurement aids of the split-half kernel, as eyoc_debug_conv_ablate / eyoc_debug_conv_times above. */
 int eyoc_debug_convh_ablate(int flags);
 int eyoc_debug_convh_times(long long* host_out_1024x6);
