@@ -757,7 +757,8 @@ int launch_h2(const HArgs& a, cudaStream_t stream) {
     EYOC_LAUNCH_CHECK();
     return EYOC_OK;
 }
-int h_wide_issuers = 1;   // MMA-issuing threads of the 128-channel kernel: 1 (one thread, probing ahead) or 2 (one per tile)
+int h_wide_issuers = 2;   // MMA-issuing threads of the 128-channel kernel: 2 (one per tile; measured 10-17 % faster on the
+                          // 128 / 256-channel levels) or 1 (one thread, probing ahead)
 template <bool WIDE, int NSW, int NXS>
 int launch_h(const HArgs& a, cudaStream_t stream) {
     if (WIDE && h_wide_issuers == 2 && !h_ablate) return launch_h2<WIDE, NSW, NXS, false, WIDE>(a, stream);

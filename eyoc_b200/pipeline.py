@@ -164,7 +164,9 @@ class RegistrationPipeline:
         rec[:, :16] = out['trans'].reshape(P, 16)
         rec[:, 16] = out['labels'].sum(1)
         rec[:, 17] = out['fitness'].argmax(1).float()
-        rec[:, 18] = torch.as_tensor(pair_ids, dtype=torch.float32, device=rec.device)
+        # (a pageable host -> device copy would synchronise the stream: pinned + non_blocking keeps the host running ahead)
+        ids = pair_ids if isinstance(pair_ids, torch.Tensor) else torch.tensor(list(pair_ids), dtype=torch.float32).pin_memory()
+        rec[:, 18] = ids.to(device=rec.device, dtype=torch.float32, non_blocking=True)
         rec[:, 19] = 1.0
         return rec
 
@@ -325,21 +327,20 @@ def _side_stream(device):
     return _SIDE[key]
 
 
-def gather_records(rec, num_pairs, group=None):
-    """The path's only collective: ONE all-gather of the per-pair records.  Every rank pads its block to
-    ceil(num_pairs / world) rows (block sizes follow from ``shard_range``, so no size exchange is needed);
-    the padding is stripped after the gather.  NCCL on GPUs, gloo in the CPU tests."""
+def gather_records(rec, num_pairs, group=None, counts=None):
+    """The path's only collective: ONE all-gather of the per-pair records.  Every rank pads its block to the largest
+    block (block sizes follow from ``shard_range`` - or from ``counts``, the pairs each rank holds, when the caller shards
+    differently - so no size exchange is needed); the padding is stripped after the gather.  NCCL on GPUs, gloo in the
+    CPU tests."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return rec
     world = dist.get_world_size(group)
-    m = -(-num_pairs // world)
+    if counts is None:
+        counts = [shard_range(num_pairs, world, r)[1] - shard_range(num_pairs, world, r)[0] for r in range(world)]
+    m = max(max(counts), 1)
     pad = torch.zeros((m, rec.shape[1]), dtype=rec.dtype, device=rec.device)
     pad[:rec.shape[0]] = rec
     buf = torch.empty((world * m, rec.shape[1]), dtype=rec.dtype, device=rec.device)
     dist.all_gather_into_tensor(buf, pad, group=group)
-    keep = []
-    for r in range(world):
-        lo, hi = shard_range(num_pairs, world, r)
-        keep.append(buf[r * m: r * m + (hi - lo)])
-    return torch.cat(keep, 0)
+    return torch.cat([buf[r * m: r * m + counts[r]] for r in range(world)], 0)
