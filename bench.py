@@ -191,7 +191,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from eyoc_b200 import _C, nn as enn, synth
-    from eyoc_b200.pipeline import (AsyncRecords, BlockUploader, PlanPrefetcher, RegistrationPipeline, gather_records,
+    from eyoc_b200.pipeline import (AsyncRecords, BlockFeeder, RegistrationPipeline, gather_records,
                                     plan_to_device)
     from eyoc_b200.scripts.SC2_PCR.SC2_PCR import Matcher
     from eyoc_b200.scripts.test_kitti import is_success, rte_rre
@@ -241,32 +241,27 @@ def run_ours(args):
     # End to end: host inputs every step.  The copies of block i + 1 (coordinates, points, the freshly drawn index plan) run on
     # a copy stream while block i computes; the all-gather and the device-to-host read of block i's records run on side
     # streams and are collected by the host one block later - the compute stream never waits for a copy or a collective.
-    prefetch = None
-    uploader = BlockUploader(dev)
+    feeder = None
     rec_hosts = [torch.empty((P * world, 24), dtype=torch.float32).pin_memory() for _ in range(2)]
     ids = list(range(rank * P, rank * P + P))
     ids_dev = torch.tensor(ids, dtype=torch.float32, device=dev)
 
-    def start_upload():
-        pl = prefetch.get()                                        # fresh host RNG draws (planned on a worker thread)
-        return uploader.start(coords=coords_h, xyz=xyz_h, fc0=pl['fc0'], fc1=pl['fc1'], src=pl['src'], tgt=pl['tgt']), pl
-
     e2e_phase = {}
 
     def run_e2e(n_steps):
-        ticket, pl = start_upload()
+        ticket, pl = feeder.get()
         pending, last = None, None
-        acc = [0.0] * 5
+        acc = [0.0] * 4
         for k in range(n_steps):
             t0_ = time.perf_counter()
             t = ticket.wait()
             plan_k = dict(pl, fc0=t['fc0'], fc1=t['fc1'], src=t['src'], tgt=t['tgt'], fc_uniform=True)
             out = pipe.run(t['coords'], t['xyz'], sizes, plan=plan_k, descriptors=desc_d)
-            ticket.release()                                       # its buffers may be refilled two blocks from now
+            ticket.release()                                       # its buffers may be refilled a few blocks from now
             t1_ = time.perf_counter()
             ar = AsyncRecords(pipe.records(out, ids_dev), P * world, host_out=rec_hosts[k & 1])
             t2_ = time.perf_counter()
-            ticket, pl = start_upload()                            # block k + 1: staged and copied while block k computes
+            ticket, pl = feeder.get()                              # block k + 1: planned, staged and copied by the feeder thread
             t3_ = time.perf_counter()
             if pending is not None:
                 last = pending.result()                            # the host blocks on block k - 1's records only
@@ -276,7 +271,7 @@ def run_ours(args):
                 acc[i_] += d_
         last = pending.result()
         e2e_phase.update(host_ms_per_step={'pipe_run_launch': 1e3 * acc[0] / n_steps, 'records_async': 1e3 * acc[1] / n_steps,
-                                           'plan_wait_and_upload_start': 1e3 * acc[2] / n_steps, 'wait_prev_records': 1e3 * acc[3] / n_steps})
+                                           'wait_for_feeder': 1e3 * acc[2] / n_steps, 'wait_prev_records': 1e3 * acc[3] / n_steps})
         return last
 
     for _ in range(W):
@@ -317,16 +312,17 @@ def run_ours(args):
     value = P * world * K / (ms / 1e3)
 
     # ---- end-to-end timing through the public API with host inputs
-    prefetch = PlanPrefetcher(pipe, (sizes for _ in range(K + 8)))         # host RNG planning of block i+1 overlaps block i
+    # the feeder thread plans (fresh host RNG draws), stages and uploads block i + 1 .. i + 2 while block i computes
+    feeder = BlockFeeder(pipe, (dict(coords=coords_h, xyz=xyz_h, sizes=sizes) for _ in range(K + 8)), dev, depth=2)
     run_e2e(2)
     barrier()
     t0 = time.perf_counter()
     rec_e2e = run_e2e(K)
     barrier()
     e2e_s = time.perf_counter() - t0
-    h2d_bytes = uploader.bytes_last
+    h2d_bytes = feeder.uploader.bytes_last
     clocks = sampler.stop()
-    prefetch.close()
+    feeder.close()
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -424,7 +420,7 @@ def run_ours(args):
             'e2e': {'value': e2e, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(h2d_bytes),
                     'd2h_bytes_per_step': int(rec_hosts[0].numel() * 4), 'ms_per_step': 1e3 * e2e_s / K,
                     'host_phases': e2e_phase.get('host_ms_per_step'),
-                    'overlap': 'H2D of block i+1 on a copy stream, all-gather + D2H of block i on side streams (read by the host one block later)'},
+                    'overlap': 'a feeder thread plans (host RNG), stages and uploads block i+1 on a copy stream; all-gather + D2H of block i on side streams, read by the host one block later'},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'features_checked': features_checked,
             'gather_checked': gather_checked,
             'accuracy': {'rr_vs_gt': succ / P, 'rte_m_median': float(np.median(rtes)), 'rre_deg_median': float(np.nanmedian(rres))}}

@@ -527,7 +527,7 @@ __device__ __forceinline__ bool seed_consensus_body(const SeedArgs& a, const int
     uint32_t* hrow = sm + W;             // [W]
     uint32_t* nzmap = sm + 2 * W;        // [W] columns with a non-zero SC2 value
     uint32_t* keys = sm + 3 * W;         // [keycap]  (count << 16) | (65535 - j)
-    __shared__ int ncand, npos, nnz, nwin;
+    __shared__ int ncand, npos, nnz, nwin, ntw;
     __shared__ unsigned int hist[256], sel_bin, sel_rem;
     __shared__ uint32_t win[MAXK];
     __shared__ int idx1[MAXK], idx2[MAXK], fine[MAXK], lval[MAXK];
@@ -539,7 +539,7 @@ __device__ __forceinline__ bool seed_consensus_body(const SeedArgs& a, const int
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k1 = a.k1, k2 = a.k2;
 
-    if (tid == 0) { ncand = 0; npos = 0; nnz = 0; nwin = 0; }
+    if (tid == 0) { ncand = 0; npos = 0; nnz = 0; nwin = 0; ntw = 0; }
     for (int w = tid; w < W; w += SC_NT) nzmap[w] = 0;
     __syncthreads();
     int nc;
@@ -572,21 +572,51 @@ __device__ __forceinline__ bool seed_consensus_body(const SeedArgs& a, const int
             }
         }
         __syncthreads();
-        // 2. SC2[seed, j] = popc(tight[seed] & tight[j]) for those columns (warp per column)
+        // 2. SC2[seed, j] = popc(tight[seed] & tight[j]) for those columns.  tight[seed] is as sparse as hard[seed] (a few
+        //    dozen bits on LiDAR data): its non-zero words are compacted (hrow is free again) and, when there are few of
+        //    them, every THREAD takes a column and walks that list - ~6 instructions per (column, word) and no shuffle
+        //    reduction, against ~80 instructions per column for a warp sweeping all W words.  Dense seed rows keep the
+        //    coalesced warp-per-column sweep (a thread-per-column walk would fetch a 32-byte sector per word).
+        uint32_t* twi = hrow;                            // word indices of the non-zero words of trow
+        for (int w = tid; w < W; w += SC_NT)
+            if (trow[w]) twi[atomicAdd(&ntw, 1)] = (uint32_t)w;
+        __syncthreads();
+        const int nzw = ntw;
         int nz = 0;
-        for (int c = warp; c < nc; c += SC_NT / 32) {
-            const uint32_t jj = 65535u - keys[c];
-            const uint32_t* row = tight + (size_t)jj * W;
-            int cn = 0;
-            for (int w = lane; w < W; w += 32) cn += __popc(trow[w] & __ldg(row + w));
-            cn = warp_sum_i(cn);
-            if (lane == 0) {
+        if (nzw <= 64) {
+            for (int c = tid; c < nc; c += SC_NT) {
+                const uint32_t jj = 65535u - keys[c];
+                const uint32_t* row = tight + (size_t)jj * W;
+                int cn = 0;
+#pragma unroll 4
+                for (int e = 0; e < nzw; ++e) {
+                    const uint32_t w = twi[e];
+                    cn += __popc(trow[w] & __ldg(row + w));
+                }
                 if (cn > 0) {
                     keys[c] = ((uint32_t)cn << 16) | (65535u - jj);
                     atomicOr(&nzmap[jj >> 5], 1u << (jj & 31));
                     ++nz;
                 } else {
                     keys[c] = 0u;
+                }
+            }
+            nz = warp_sum_i(nz);
+        } else {
+            for (int c = warp; c < nc; c += SC_NT / 32) {
+                const uint32_t jj = 65535u - keys[c];
+                const uint32_t* row = tight + (size_t)jj * W;
+                int cn = 0;
+                for (int w = lane; w < W; w += 32) cn += __popc(trow[w] & __ldg(row + w));
+                cn = warp_sum_i(cn);
+                if (lane == 0) {
+                    if (cn > 0) {
+                        keys[c] = ((uint32_t)cn << 16) | (65535u - jj);
+                        atomicOr(&nzmap[jj >> 5], 1u << (jj & 31));
+                        ++nz;
+                    } else {
+                        keys[c] = 0u;
+                    }
                 }
             }
         }

@@ -223,13 +223,14 @@ class BlockUploader:
             ev.record()                                     # on the compute stream: everything that reads the buffers is queued
             self.owner._free[self.slot] = ev
 
-    def __init__(self, device):
+    def __init__(self, device, slots=2):
         self.device = device
         self.stream = torch.cuda.Stream(device=device)
-        self._pinned = [{}, {}]
-        self._dev = [{}, {}]
-        self._free = [None, None]       # compute-stream events: the device buffers of a set may be overwritten
-        self._copied = [None, None]     # copy-stream events: the pinned staging buffers of a set may be overwritten
+        self.slots = slots
+        self._pinned = [{} for _ in range(slots)]
+        self._dev = [{} for _ in range(slots)]
+        self._free = [None] * slots       # compute-stream events: the device buffers of a set may be overwritten
+        self._copied = [None] * slots     # copy-stream events: the pinned staging buffers of a set may be overwritten
         self._flip = 0
         self.bytes_last = 0
 
@@ -243,7 +244,7 @@ class BlockUploader:
     def start(self, **host):
         """host: name -> numpy array / CPU tensor (or a list of equally shaped arrays, stacked).  Returns a ticket."""
         slot = self._flip
-        self._flip ^= 1
+        self._flip = (self._flip + 1) % self.slots
         pinned, devp = self._pinned[slot], self._dev[slot]
         out, nbytes = {}, 0
         with torch.cuda.stream(self.stream):
@@ -271,6 +272,45 @@ class BlockUploader:
         self._copied[slot] = ev
         self.bytes_last = nbytes
         return BlockUploader._Ticket(self, slot, out, ev)
+
+
+class BlockFeeder:
+    """Everything the host does for a block BEFORE its kernels are launched - the RNG index plan (``pipe.plan``), the
+    pinned staging of the plan arrays and the host -> device copies of coordinates / points / plan on the copy stream - on a
+    worker thread, ``depth`` blocks ahead of the compute loop.  ``get()`` returns (ticket, plan) in block order (the global
+    numpy RNG stream is consumed exactly as by a sequential loop); the main thread only launches kernels.
+    ``blocks`` yields dicts with ``coords`` / ``xyz`` (pinned CPU tensors or numpy arrays) and ``sizes``."""
+
+    def __init__(self, pipe, blocks, device, depth=2):
+        import queue
+        import threading
+        self.q = queue.Queue(maxsize=depth)
+        self.uploader = BlockUploader(device, slots=depth + 2)      # a set is reused only after its block was consumed
+        self._stop = False
+
+        def work():
+            torch.cuda.set_device(device)
+            for blk in blocks:
+                if self._stop:
+                    break
+                pl = pipe.plan(blk['sizes'])
+                ticket = self.uploader.start(coords=blk['coords'], xyz=blk['xyz'], fc0=pl['fc0'], fc1=pl['fc1'], src=pl['src'],
+                                             tgt=pl['tgt'])
+                self.q.put((ticket, pl))
+            self.q.put(None)
+        self.t = threading.Thread(target=work, daemon=True)
+        self.t.start()
+
+    def get(self):
+        return self.q.get()
+
+    def close(self):
+        self._stop = True
+        try:
+            while self.q.get_nowait() is not None:
+                pass
+        except Exception:      # noqa: BLE001
+            pass
 
 
 class AsyncRecords:
