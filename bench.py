@@ -313,6 +313,7 @@ def run_ours(args):
 
     # ---- end-to-end timing through the public API with host inputs
     # the feeder thread plans (fresh host RNG draws), stages and uploads block i + 1 .. i + 2 while block i computes
+    sys.setswitchinterval(2e-4)            # two Python threads (feeder, launcher): hand the GIL over quickly
     feeder = BlockFeeder(pipe, (dict(coords=coords_h, xyz=xyz_h, sizes=sizes) for _ in range(K + 8)), dev, depth=2)
     run_e2e(2)
     barrier()

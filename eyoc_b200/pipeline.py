@@ -51,8 +51,8 @@ def plan_to_device(plan, device):
     """Upload the index arrays of a plan once (benchmark 'inputs resident in HBM' mode)."""
     out = dict(plan)
     if plan['fc_uniform']:
-        out['fc0'] = torch.from_numpy(np.stack(plan['fc0'])).to(device)
-        out['fc1'] = torch.from_numpy(np.stack(plan['fc1'])).to(device)
+        out['fc0'] = torch.from_numpy(np.ascontiguousarray(np.stack(plan['fc0']) if isinstance(plan['fc0'], list) else plan['fc0'])).to(device)
+        out['fc1'] = torch.from_numpy(np.ascontiguousarray(np.stack(plan['fc1']) if isinstance(plan['fc1'], list) else plan['fc1'])).to(device)
     else:
         out['fc0'] = [torch.from_numpy(a).to(device) for a in plan['fc0']]
         out['fc1'] = [torch.from_numpy(a).to(device) for a in plan['fc1']]
@@ -114,7 +114,7 @@ class RegistrationPipeline:
         _C.check(_C.lib().eyoc_plan_draws(vp(key), ctypes.byref(pos_c), ctypes.c_int(P), vp(n0), vp(n1), vp(offs),
                                           ctypes.c_int(sub), ctypes.c_int(ns), ctypes.c_int(nn_), vp(fc0), vp(fc1), vp(src), vp(tgt)))
         np.random.set_state((name, key, int(pos_c.value), has_gauss, cached))
-        return dict(offsets=offs, fc0=list(fc0), fc1=list(fc1), src=src, tgt=tgt, fc_uniform=True)
+        return dict(offsets=offs, fc0=fc0, fc1=fc1, src=src, tgt=tgt, fc_uniform=True)      # fc0 / fc1 [P, subsample] arrays
 
     def run(self, coords, xyz, sizes, plan=None, descriptors=None):
         """coords [sum N, 4] int32 (batch column = cloud id 0..2P-1), xyz [sum N, 3] fp32, both CUDA, clouds
@@ -135,8 +135,8 @@ class RegistrationPipeline:
         out = {'features': F}
         if self.run_find_corr:                                   # diagnostic NN of the reference (test_kitti.py:153-154)
             if plan['fc_uniform']:
-                i0 = dv(plan['fc0'] if isinstance(plan['fc0'], torch.Tensor) else np.stack(plan['fc0']))
-                i1 = dv(plan['fc1'] if isinstance(plan['fc1'], torch.Tensor) else np.stack(plan['fc1']))
+                i0 = dv(plan['fc0'] if isinstance(plan['fc0'], (torch.Tensor, np.ndarray)) else np.stack(plan['fc0']))
+                i1 = dv(plan['fc1'] if isinstance(plan['fc1'], (torch.Tensor, np.ndarray)) else np.stack(plan['fc1']))
                 nn_idx = knn1(Fm[i0], Fm[i1], form=0)
                 out['find_corr_src'] = i0
                 out['find_corr_tgt'] = torch.gather(i1, 1, nn_idx)
