@@ -61,6 +61,17 @@ def plan_to_device(plan, device):
     return out
 
 
+def gather_rows(src, idx):
+    """src [n, c] fp32 CUDA, idx int64 [...] CUDA -> src[idx] of shape [..., c] (eyoc_gather_rows: one coalesced launch)."""
+    src = _C.f32c(src)
+    idx = idx.contiguous()
+    out = torch.empty(tuple(idx.shape) + (src.shape[1],), dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        _C.check(_C.lib().eyoc_gather_rows(_C.ptr(src), _C.ptr(idx), _C.c_int64(idx.numel()), _C.c_int(src.shape[1]), _C.ptr(out),
+                                           _C.stream()))
+    return out
+
+
 class RegistrationPipeline:
     """features -> matching -> SC2-PCR for blocks of pairs on one GPU."""
 
@@ -137,7 +148,7 @@ class RegistrationPipeline:
             if plan['fc_uniform']:
                 i0 = dv(plan['fc0'] if isinstance(plan['fc0'], (torch.Tensor, np.ndarray)) else np.stack(plan['fc0']))
                 i1 = dv(plan['fc1'] if isinstance(plan['fc1'], (torch.Tensor, np.ndarray)) else np.stack(plan['fc1']))
-                nn_idx = knn1(Fm[i0], Fm[i1], form=0)
+                nn_idx = knn1(gather_rows(Fm, i0), gather_rows(Fm, i1), form=0)
                 out['find_corr_src'] = i0
                 out['find_corr_tgt'] = torch.gather(i1, 1, nn_idx)
             else:
@@ -148,9 +159,9 @@ class RegistrationPipeline:
                     t_.append(b[knn1(Fm[a], Fm[b], form=0)])
                 out['find_corr_src'], out['find_corr_tgt'] = s_, t_
         src_idx, tgt_idx = dv(plan['src']), dv(plan['tgt'])      # [P, num_node]
-        nn_idx = knn1(Fm[src_idx], Fm[tgt_idx], form=1)          # SC2_PCR.py:296-298
+        nn_idx = knn1(gather_rows(Fm, src_idx), gather_rows(Fm, tgt_idx), form=1)          # SC2_PCR.py:296-298
         corr_tgt = torch.gather(tgt_idx, 1, nn_idx)
-        src_corr, tgt_corr = xyz[src_idx], xyz[corr_tgt]
+        src_corr, tgt_corr = gather_rows(xyz, src_idx), gather_rows(xyz, corr_tgt)
         trans, fitness, labels = self.matcher._run(src_corr, tgt_corr, want_labels=True)
         out.update(trans=trans, labels=labels, fitness=fitness, src_corr_idx=src_idx, tgt_corr_idx=corr_tgt,
                    src_corr=src_corr, tgt_corr=tgt_corr)

@@ -33,6 +33,11 @@ int eyoc_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 /* number of kernels this library has launched in this process (bench.py reports it as gpu_launches) */
 unsigned long long eyoc_launch_count(void);
 
+/* Row gather out[i, :] = src[idx[i], :] (src [n, c] fp32, idx [m] int64 -> out [m, c]): the index compositions of
+ * scripts/test_kitti.py:36-42,69-73 (find_corr, random_sample) and scripts/SC2_PCR/SC2_PCR.py:290-305 (match_pair) for a
+ * whole block of pairs in one launch. */
+int eyoc_gather_rows(const float* src, const int64_t* idx, int64_t m, int c, float* out, eyoc_stream_t stream);
+
 /* ---------------------------------------------------------------- nearest neighbour matching
  * Replaces lib/eval.py:18-48 find_nn_gpu (+ lib/metrics.py:26-27 pdist 'SquareL2')  [form 0]
  * and the matching core of scripts/SC2_PCR/SC2_PCR.py:296-298 Matcher.match_pair       [form 1].
