@@ -19,7 +19,7 @@ from tests.test_conv_tc_gpu import _ref  # noqa: E402
 
 def main():
     lib = _C.lib()
-    for c0, cout, n_in, n_out, cap in ((64, 64, 6000, 24000, 4), (128, 256, 3000, 12000, 2)):
+    for c0, cout, n_in, n_out, cap in ((64, 64, 2000, 6144, 2), (128, 256, 1000, 3072, 1)):
         g = torch.Generator().manual_seed(c0 + cout)
         K = 27
         x = torch.randn(n_in, c0, generator=g).cuda()
