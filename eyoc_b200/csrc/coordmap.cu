@@ -319,18 +319,15 @@ __global__ void parity_class_kernel(const int* __restrict__ coords, int n, int t
 // Rows sorted by this key put rows with the same neighbour pattern into the same 128-row tile, so most
 // (tile, offset) items of the tensor-core convolution are either skipped or densely filled, while a group of
 // clouds (the L2 working set of the gather) stays contiguous.
-struct RowMap { int r[27]; };      // row of the source table that holds kernel offset k (identity, or the 3^3 sub-cube of a 5^3 table)
-
 __global__ void tile_key_kernel(const int* __restrict__ nbr, int K, int n_out, const int* __restrict__ coords, int group,
-                                unsigned long long* __restrict__ keys, int* __restrict__ iota, unsigned int* __restrict__ hist,
-                                RowMap rows) {
+                                unsigned long long* __restrict__ keys, int* __restrict__ iota, unsigned int* __restrict__ hist) {
     __shared__ unsigned int h_s[32];
     if (threadIdx.x < 32) h_s[threadIdx.x] = 0;
     __syncthreads();
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int m = 0;
     if (o < n_out) {
-        for (int k = 0; k < K; ++k) m |= (unsigned int)(__ldg(nbr + (size_t)rows.r[k] * n_out + o) >= 0) << k;
+        for (int k = 0; k < K; ++k) m |= (unsigned int)(__ldg(nbr + (size_t)k * n_out + o) >= 0) << k;
         const int b = coords[4 * (size_t)o];
         keys[o] = ((unsigned long long)(unsigned int)(b / group) << 27) | m;
         iota[o] = o;
@@ -369,12 +366,11 @@ __global__ void tile_key_remap_kernel(unsigned long long* __restrict__ keys, int
     keys[o] = (key & ~0x7ffffffull) | r;
 }
 
-__global__ void permute_columns_kernel(const int* __restrict__ nbr, int n_out, const int* __restrict__ perm, int* __restrict__ out,
-                                       RowMap rows) {
+__global__ void permute_columns_kernel(const int* __restrict__ nbr, int n_out, const int* __restrict__ perm, int* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_out) return;
     const size_t k = blockIdx.y;
-    out[k * n_out + i] = __ldg(nbr + (size_t)rows.r[k] * n_out + __ldg(perm + i));
+    out[k * n_out + i] = __ldg(nbr + k * n_out + __ldg(perm + i));
 }
 
 }  // namespace
@@ -388,20 +384,7 @@ extern "C" size_t eyoc_tile_order_workspace_bytes(int64_t n_out) {
 
 extern "C" int eyoc_tile_order(const int32_t* nbr, int K, int64_t n_out, const int32_t* out_coords, int group_clouds, int max_batch,
                                int32_t* row_perm, int32_t* nbr_tiled, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-    return eyoc_tile_order_sub(nbr, K, 0, n_out, out_coords, group_clouds, max_batch, row_perm, nbr_tiled, workspace, workspace_bytes, stream);
-}
-
-extern "C" int eyoc_tile_order_sub(const int32_t* nbr, int K, int src_ksize, int64_t n_out, const int32_t* out_coords, int group_clouds,
-                                   int max_batch, int32_t* row_perm, int32_t* nbr_tiled, void* workspace, size_t workspace_bytes,
-                                   cudaStream_t stream) {
     EYOC_CHECK_ARG(nbr && out_coords && row_perm && nbr_tiled, "eyoc_tile_order: null argument");
-    EYOC_CHECK_ARG(src_ksize == 0 || (K == 27 && (src_ksize == 5 || src_ksize == 7)), "eyoc_tile_order_sub: a 3^3 map out of a 5^3 / 7^3 table only");
-    RowMap rows;
-    for (int k = 0; k < 27; ++k) rows.r[k] = k;
-    if (src_ksize) {        // offset (ix, iy, iz) - 1 of the 3^3 kernel sits at (ix, iy, iz) - 1 + r of the larger one
-        const int S = src_ksize, sh = (src_ksize - 3) / 2;
-        for (int k = 0; k < 27; ++k) rows.r[k] = (k % 3 + sh) + S * ((k / 3) % 3 + sh + S * (k / 9 + sh));
-    }
     EYOC_CHECK_ARG(K >= 1 && K <= 27 && group_clouds >= 1 && max_batch >= 0 && max_batch <= 65535, "eyoc_tile_order: bad K / group / batch");
     EYOC_CHECK_ARG(n_out >= 0 && n_out < (1ll << 31), "eyoc_tile_order: bad n_out");
     if (n_out == 0) return EYOC_OK;
@@ -420,7 +403,7 @@ extern "C" int eyoc_tile_order_sub(const int32_t* nbr, int K, int src_ksize, int
     unsigned int* hist = c.take<unsigned int>(32);
     int* pos = c.take<int>(32);
     EYOC_CUDA(cudaMemsetAsync(hist, 0, 32 * sizeof(unsigned int), stream));
-    tile_key_kernel<<<g, 256, 0, stream>>>(nbr, K, (int)n_out, out_coords, group_clouds, keys, iota, hist, rows);
+    tile_key_kernel<<<g, 256, 0, stream>>>(nbr, K, (int)n_out, out_coords, group_clouds, keys, iota, hist);
     EYOC_LAUNCH_CHECK();
     tile_bit_order_kernel<<<1, 32, 0, stream>>>(hist, K, pos);
     EYOC_LAUNCH_CHECK();
@@ -430,7 +413,7 @@ extern "C" int eyoc_tile_order_sub(const int32_t* nbr, int K, int src_ksize, int
     while ((max_batch / group_clouds) >> gbits) ++gbits;
     EYOC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, temp, keys, keys2, iota, row_perm, (int)n_out, 0, 27 + gbits, stream));
     g_eyoc_launches += 4;
-    permute_columns_kernel<<<dim3(g, K), 256, 0, stream>>>(nbr, (int)n_out, row_perm, nbr_tiled, rows);
+    permute_columns_kernel<<<dim3(g, K), 256, 0, stream>>>(nbr, (int)n_out, row_perm, nbr_tiled);
     EYOC_LAUNCH_CHECK();
     return EYOC_OK;
 }

@@ -155,28 +155,21 @@ class CoordinateManager:
         (csrc/coordmap.cu: eyoc_tile_order).  The cloud group bounds the gather's L2 working set."""
         key = (ts_in, ts_out, ksize, transposed)
         if key not in self._tiled:
-            # a 3^3 stride-1 map is the central sub-cube of a 5^3 / 7^3 table of the same level: no probing of its own
-            src_ksize = 0
-            if ksize == 3 and ts_in == ts_out and not transposed and key not in self._maps:
-                for big in (5, 7):
-                    if (ts_in, ts_out, big, False) in self._maps:
-                        src_ksize = big
-                        break
-            nbr = self._maps[(ts_in, ts_out, src_ksize, False)] if src_ksize else self.kernel_map(ts_in, ts_out, ksize, transposed)
+            nbr = self.kernel_map(ts_in, ts_out, ksize, transposed)
             self._check_status()
             lin, lout = self.levels[ts_in], self.levels[ts_out]
-            K, n_out = (ksize ** 3 if src_ksize else nbr.shape[0]), nbr.shape[1]
+            K, n_out = nbr.shape
             rows_per_cloud = max(1, lin.n // (self.max_batch + 1))
             cin_hint = min(256, 64 * ts_in)          # widest input the maps of this level feed (ResUNet channel table)
             group = max(1, min(self.max_batch + 1, int(TILE_GROUP_BYTES // (rows_per_cloud * 4 * cin_hint))))
             perm = torch.empty(n_out, dtype=torch.int32, device=self.device)
-            tiled = torch.empty((K, n_out), dtype=torch.int32, device=self.device)
+            tiled = torch.empty_like(nbr)
             lib = _C.lib()
             ws = torch.empty(max(lib.eyoc_tile_order_workspace_bytes(_C.c_int64(n_out)), 8), dtype=torch.uint8, device=self.device)
             with torch.cuda.device(self.device):
-                _C.check(lib.eyoc_tile_order_sub(_C.ptr(nbr), _C.c_int(K), _C.c_int(src_ksize), _C.c_int64(n_out), _C.ptr(lout.coords),
-                                                 _C.c_int(group), _C.c_int(self.max_batch), _C.ptr(perm), _C.ptr(tiled), _C.ptr(ws),
-                                                 _C.c_size_t(ws.numel()), _C.stream()))
+                _C.check(lib.eyoc_tile_order(_C.ptr(nbr), _C.c_int(K), _C.c_int64(n_out), _C.ptr(lout.coords), _C.c_int(group),
+                                             _C.c_int(self.max_batch), _C.ptr(perm), _C.ptr(tiled), _C.ptr(ws),
+                                             _C.c_size_t(ws.numel()), _C.stream()))
             self._tiled[key] = (tiled, perm)
         return self._tiled[key]
 

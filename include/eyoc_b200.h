@@ -170,12 +170,6 @@ int eyoc_kernel_map_transpose(const int32_t* nbr_down, int64_t n_coarse, int64_t
 size_t eyoc_tile_order_workspace_bytes(int64_t n_out);
 int eyoc_tile_order(const int32_t* nbr, int K, int64_t n_out, const int32_t* out_coords, int group_clouds, int max_batch,
                     int32_t* row_perm, int32_t* nbr_tiled, void* workspace, size_t workspace_bytes, eyoc_stream_t stream);
-/* The same for a 3^3 stride-1 map taken out of a LARGER stride-1 table of the same coordinate set (src_ksize 5 or 7; 0 = nbr
- * is the 3^3 table itself): its offsets are the central sub-cube of the larger kernel, so the level-1 map of the residual
- * blocks needs no probing of its own once conv1's 5^3 table exists (model/resunet.py:31,41). */
-int eyoc_tile_order_sub(const int32_t* nbr, int K, int src_ksize, int64_t n_out, const int32_t* out_coords, int group_clouds,
-                        int max_batch, int32_t* row_perm, int32_t* nbr_tiled, void* workspace, size_t workspace_bytes,
-                        eyoc_stream_t stream);
 /* cls[i] = parity class (3 bits) of coords[i] / ts: groups the rows of a transposed stride-2 convolution by
  * their set of admissible kernel offsets. */
 int eyoc_parity_class(const int32_t* coords, int64_t n, int ts, int32_t* cls, eyoc_stream_t stream);
@@ -252,6 +246,12 @@ int eyoc_debug_convh_times(long long* host_out_1024x6);
 /* bit 4 of the flags: CTAs 200..203 record clock64 per work item (first 96) at {producer: empty-wait start, end, arrival;
  * MMA thread: full-wait start, end, after commit}. */
 int eyoc_debug_convh_trace(long long* host_out_4x96x6);
+
+/* Development probe of the TMA row gather (cp.async.bulk.tensor.2d tile::gather4; csrc/gather4_probe.cu): `ctas` CTAs each gather
+ * 256 rows of X [n_rows, 64] fp16 by index into a SWIZZLE_128B stage `reps` times; out = CTA 0's last stage (32 KB),
+ * cycles [ctas] = clock64 spent.  tools/gather4_probe.py checks the layout and prints the rate. */
+int eyoc_debug_gather4_probe(const void* X, int64_t n_rows, const int32_t* idx, int n_idx, int ctas, int reps, int box_rows, void* out,
+                             long long* cycles, eyoc_stream_t stream);
 
 /* ---------------------------------------------------------------- robust linearised pose (validation path)
  * util/transform_estimation.py:89-116 est_quad_linear_robust: `iterations` (reference: 20) rounds of a weighted small-angle
