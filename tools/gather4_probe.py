@@ -19,14 +19,15 @@ def main():
     lib = _C.lib()
     dev = torch.device('cuda', 0)
     g = torch.Generator().manual_seed(0)
-    n_rows = 3_000_000
+    n_rows = int(os.environ.get('G4_ROWS', 3_000_000))
     X = torch.randn(n_rows, 64, generator=g).half().to(dev)
     n_idx = 256 * 4096
     idx = torch.randint(0, n_rows, (n_idx,), generator=g, dtype=torch.int32)
     idx[torch.rand(n_idx, generator=g) < 0.2] = -1
     idx_d = idx.to(dev)
-    for box_rows in (1, 4):
-        for ctas, reps in ((1, 1), (148, 200)):
+    # configuration = issuing warps x stages in flight (1: 1x1, 102: 1x6, 2: 2x6, 4: 4x6, 8: 8x6, 16: 16x6, 116: 16x1)
+    for box_rows in (1, 102, 2, 4, 8, 16, 116):
+        for ctas, reps in ((148, 240),):
             out = torch.zeros(256 * 64, dtype=torch.float16, device=dev)
             cyc = torch.zeros(ctas, dtype=torch.int64, device=dev)
             rc = lib.eyoc_debug_gather4_probe(_C.ptr(X), ctypes.c_int64(n_rows), _C.ptr(idx_d), ctypes.c_int(n_idx), ctypes.c_int(ctas),
@@ -37,7 +38,7 @@ def main():
             try:
                 torch.cuda.synchronize()
             except RuntimeError as e:
-                print(f'box_rows {box_rows} ctas {ctas}: kernel failed: {e}')
+                print(f'config {box_rows} ctas {ctas}: kernel failed: {e}')
                 return
             last = ((0 * reps + reps - 1) % (n_idx // 256)) * 256
             rows = idx[last:last + 256].long()
@@ -50,7 +51,7 @@ def main():
             good = bool(torch.equal(unsw, want))
             plain = bool(torch.equal(stage.reshape(256, 64), want))
             cy = cyc.cpu().numpy()
-            print(f'box_rows {box_rows} ctas {ctas} reps {reps}: swizzled layout correct {good} (unswizzled {plain}); '
+            print(f'config {box_rows} ctas {ctas} reps {reps}: swizzled layout correct {good} (unswizzled {plain}); '
                   f'{float(np.median(cy)) / reps:.0f} cycles per 256-row stage (median over CTAs)')
 
 
