@@ -45,7 +45,44 @@ TILE_GROUP_BYTES = 4e9
 
 
 class _Level:
-    __slots__ = ('coords', 'n', 'keys', 'vals', 'cap', 'ts')
+    __slots__ = ('coords', 'n', 'keys', 'vals', 'cap', 'ts', 'n_read', 'coords_buf')
+
+
+_PINNED_POOL = []
+_SIDE_STREAMS = {}
+
+
+class _AsyncRead:
+    """A few int32 values on their way to the host, copied on a side stream right behind the kernel that produced them.
+    ``.item()`` / ``.tolist()`` append their copy to the END of the launching stream and so wait for everything queued since;
+    this read completes as soon as its producer has, however much work the launching stream has been given meanwhile - the
+    host can keep the GPU's queue full across the data-dependent sizes of the coordinate levels."""
+
+    def __init__(self, src):
+        dev = src.device
+        key = (dev.type, dev.index)
+        if key not in _SIDE_STREAMS:
+            _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+        side = _SIDE_STREAMS[key]
+        self.n = src.numel()
+        self.host = _PINNED_POOL.pop() if _PINNED_POOL else torch.empty(8, dtype=torch.int32).pin_memory()
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            self.host[:self.n].copy_(src.reshape(-1), non_blocking=True)
+            self.done = torch.cuda.Event()
+            self.done.record(side)
+        src.record_stream(side)
+        self.values = None
+
+    def get(self):
+        if self.values is None:
+            self.done.synchronize()
+            self.values = self.host[:self.n].tolist()
+            _PINNED_POOL.append(self.host)
+            self.host = None
+        return self.values
 
 
 class CoordinateManager:
@@ -77,44 +114,63 @@ class CoordinateManager:
                                               _C.c_int64(lv.cap), _C.ptr(self._status), _C.stream()))
         self.levels[1] = lv
         self._checked = False
+        self._pending = {}
+        self._status_read = _AsyncRead(self._status[:2])
+        if lv.n > 0:
+            self._start_level(2)            # queued right behind the hash build: its size is on the host long before it is needed
 
     # ------------------------------------------------------------------ levels
     def _check_status(self):
         if not self._checked:
-            st, self.max_batch = (int(v) for v in self._status[:2].tolist())
+            st, self.max_batch = (int(v) for v in self._status_read.get())
             if st & 1:
                 raise RuntimeError('coordinates outside the packed 16-bit range (batch 0..65535, xyz -32768..32767)')
             if st & 2:
                 raise RuntimeError('duplicate coordinates: quantise first (sparse_quantize)')
             self._checked = True
 
-    def ensure_levels(self, max_stride):
-        """Build the stride-2 coordinate sets up to ``max_stride`` (one 4-byte D2H read per new level: the row
-        count sizes the next level's buffers, as in MinkowskiEngine's host-side coordinate manager)."""
-        ts = 1
+    def _start_level(self, ts2):
+        """Queue the kernels of the stride-``ts2`` coordinate set (needs the finer level's row count on the host); its own
+        row count travels back through an _AsyncRead."""
+        fine = self.levels[ts2 // 2]
         lib = _C.lib()
+        lv = _Level()
+        lv.ts = ts2
+        lv.cap = _pow2_at_least(2 * max(fine.n, 1))
+        lv.keys = torch.empty(lv.cap, dtype=torch.int64, device=self.device)
+        lv.vals = torch.empty(lv.cap, dtype=torch.int32, device=self.device)
+        lv.coords_buf = torch.empty((fine.n, 4), dtype=torch.int32, device=self.device)
+        n_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        ws = torch.empty(max(lib.eyoc_downsample_workspace_bytes(_C.c_int64(fine.n)), 8), dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
-            while ts < max_stride:
-                fine = self.levels[ts]
-                ts2 = ts * 2
-                if ts2 not in self.levels:
-                    lv = _Level()
-                    lv.ts = ts2
-                    lv.cap = _pow2_at_least(2 * max(fine.n, 1))
-                    lv.keys = torch.empty(lv.cap, dtype=torch.int64, device=self.device)
-                    lv.vals = torch.empty(lv.cap, dtype=torch.int32, device=self.device)
-                    coords = torch.empty((fine.n, 4), dtype=torch.int32, device=self.device)
-                    n_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
-                    ws = torch.empty(max(lib.eyoc_downsample_workspace_bytes(_C.c_int64(fine.n)), 8), dtype=torch.uint8,
-                                     device=self.device)
-                    _C.check(lib.eyoc_coords_downsample(_C.ptr(fine.coords), _C.c_int64(fine.n), _C.c_int(ts2),
-                                                        _C.ptr(lv.keys), _C.ptr(lv.vals), _C.c_int64(lv.cap),
-                                                        _C.ptr(coords), _C.ptr(n_dev), _C.ptr(ws),
-                                                        _C.c_size_t(ws.numel()), _C.stream()))
-                    lv.n = int(n_dev.item())
-                    lv.coords = coords[:lv.n]
-                    self.levels[ts2] = lv
-                ts = ts2
+            _C.check(lib.eyoc_coords_downsample(_C.ptr(fine.coords), _C.c_int64(fine.n), _C.c_int(ts2), _C.ptr(lv.keys),
+                                                _C.ptr(lv.vals), _C.c_int64(lv.cap), _C.ptr(lv.coords_buf), _C.ptr(n_dev), _C.ptr(ws),
+                                                _C.c_size_t(ws.numel()), _C.stream()))
+            lv.n_read = _AsyncRead(n_dev)
+        self._pending[ts2] = lv
+
+    def _finish_level(self, ts2):
+        lv = self._pending.pop(ts2)
+        lv.n = int(lv.n_read.get()[0])
+        lv.coords = lv.coords_buf[:lv.n]
+        lv.n_read = lv.coords_buf = None
+        self.levels[ts2] = lv
+        if ts2 < self.EAGER_MAX_STRIDE and lv.n > 0:
+            self._start_level(ts2 * 2)      # the next level is queued as soon as this one's size is known
+
+    EAGER_MAX_STRIDE = 8                    # the ResUNets go down to tensor stride 8 (model/resunet.py:70)
+
+    def ensure_levels(self, max_stride):
+        """Build the stride-2 coordinate sets up to ``max_stride``.  Every level is QUEUED one level ahead of its first use
+        and its row count (which sizes the next level's buffers, as in MinkowskiEngine's host-side coordinate manager) comes
+        back through a side-stream read, so the host does not drain the GPU's queue to learn it."""
+        ts2 = 2
+        while ts2 <= max_stride:
+            if ts2 not in self.levels:
+                if ts2 not in self._pending:
+                    self._start_level(ts2)
+                self._finish_level(ts2)
+            ts2 *= 2
         self._check_status()
 
     def num_rows(self, ts):
