@@ -66,10 +66,24 @@ def test_full_kitti_configuration_vs_oracle():
             assert _nn_mismatch_is_near_tie(F0[inds0], F1, got_rows, want_rows) <= 5
         x0, f0 = MO.random_sample(p['xyz0'], F0, 5000)
         x1, f1 = MO.random_sample(p['xyz1'], F1, 5000)
+        det = {}
         T_o, lab_o, sc_o, tc_o, _ = O.estimator(torch.from_numpy(x0)[None], torch.from_numpy(x1)[None], f0[None], f1[None], ocfg,
-                                                dense_weight=False)
-        assert torch.equal(out['src_corr'][j].cpu(), sc_o[0]) and torch.equal(out['tgt_corr'][j].cpu(), tc_o[0])
-        assert int((out['labels'][j].cpu() != lab_o[0]).sum()) == 0
+                                                det, dense_weight=False)
+        assert torch.equal(out['src_corr'][j].cpu(), sc_o[0])
+        # the oracle's matching goes through torch.matmul (MKL): its summation order - and with it the winner of an fp32
+        # near-tie - can change with the alignment of its buffers from run to run (observed: 1 run in 5 flips one row).  Rows
+        # whose correspondence differs must be such near-ties (a handful at most); everything else is compared bit for bit.
+        same = (out['tgt_corr'][j].cpu() == tc_o[0]).all(1)
+        if not bool(same.all()):
+            rows = torch.nonzero(~same).flatten().tolist()
+            assert len(rows) <= 3, len(rows)
+            fs, ft = f0[det['src_sel']].double(), f1[det['tgt_sel']].double()
+            tk = torch.from_numpy(x1)[det['tgt_sel']]
+            for r in rows:
+                c_mine = int(torch.nonzero((tk == out['tgt_corr'][j][r].cpu()).all(1))[0])
+                c_or = int(det['nn_idx'][r])
+                assert abs(float(fs[r] @ ft[c_mine]) - float(fs[r] @ ft[c_or])) <= 2e-6, (r, c_mine, c_or)
+        assert int((out['labels'][j].cpu() != lab_o[0])[same].sum()) == 0
         T = out['trans'][j].cpu()
         assert float(torch.linalg.norm(T[:3, :3] - T_o[0, :3, :3])) < 1e-4
         assert float(torch.linalg.norm(T[:3, 3] - T_o[0, :3, 3])) < 1e-3
