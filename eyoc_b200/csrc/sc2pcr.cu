@@ -436,6 +436,178 @@ power_step_kernel(const Pt* __restrict__ P, const uint32_t* __restrict__ hard, i
     }
 }
 
+// The whole power iteration of one pair in ONE launch: a cluster of PF_C CTAs per pair, each owning n / PF_C rows.
+// A CTA keeps the iterate v (all n entries) and as much of its CSR slice as fits in shared memory (the rest streams from
+// L2), computes u = M v for its rows with 8 lanes per row, and pushes every u_i into all PF_C CTAs' shared memory
+// (distributed shared memory stores); after one cluster barrier each CTA normalises the full u and applies the
+// torch.allclose stopping rule redundantly, so all CTAs of the cluster take the same decision and no global round trip
+// or relaunch separates two iterations.  The per-row sums, the norm and the division are evaluated in exactly the order
+// of power_step_kernel (lane l of its warp = accumulator l / 8 of lane l % 8 here; the xor butterfly is commutative), so
+// the two kernels return the same bits.  u is double-buffered: a CTA reaches its pushes of iteration t + 2 only after the
+// barrier of t + 1, which every CTA passes after it has finished reading the buffer of iteration t.
+constexpr int PF_C = 8;
+constexpr int PF_NT = 512;
+int g_power_fused = 1;              // eyoc_debug_sc2_power_fused: 0 = one power_step_kernel launch per iteration
+
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr int PF_SMEM_MAX = 227 * 1024;
+
+struct PfArgs {
+    const Pt* P;
+    const uint32_t* hard;
+    int n, W;
+    float d_sq;
+    int num_iterations;
+    float* conf;
+    int* done;
+    int* iters;
+    Csr csr;
+    int rows_per;       // ceil(n / PF_C)
+    int n_pad;          // n rounded up to 4
+    int cache_cap;      // CSR entries of the slice kept in shared memory
+};
+
+__device__ __forceinline__ float pf_bits_lane(const Pt* P, const uint32_t* row, const Pt& me, int W, float d_sq, int vlane,
+                                              const float* v) {
+    float acc = 0.f;
+    for (int w = vlane; w < W; w += 32) {
+        uint32_t m = __ldg(row + w);
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            const int j = w * 32 + bit;
+            const float c = cross_dist(me, load_pt(P + j));
+            const float sc = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fmul_rn(c, c), d_sq)), 0.f);
+            acc = __fmaf_rn(sc, v[j], acc);
+        }
+    }
+    return acc;
+}
+
+__global__ void __cluster_dims__(PF_C, 1, 1) __launch_bounds__(PF_NT, 1)
+power_fused_kernel(const PfArgs a) {
+    extern __shared__ __align__(16) unsigned char pf_smem[];
+    const int b = blockIdx.y, n = a.n;
+    const unsigned rank = cluster_ctarank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* v = reinterpret_cast<float*>(pf_smem);
+    float* ubuf = v + a.n_pad;                                  // [2][n_pad]
+    uint32_t* rp = reinterpret_cast<uint32_t*>(ubuf + 2 * a.n_pad);          // [rows_per + 1]
+    float* cvals = reinterpret_cast<float*>(rp + ((a.rows_per + 1 + 3) & ~3));
+    uint16_t* ccols = reinterpret_cast<uint16_t*>(cvals + a.cache_cap);
+    __shared__ double red[8];
+    __shared__ int cached_rows_s;
+
+    const Pt* P = a.P + (size_t)b * n;
+    const uint32_t* hard = a.hard + (size_t)b * n * a.W;
+    const int r0 = min(n, (int)rank * a.rows_per), r1 = min(n, r0 + a.rows_per);
+    const bool ok = a.csr.ok[b] != 0;
+    const uint16_t* gcols = a.csr.cols + (size_t)b * a.csr.cap;
+    const float* gvals = a.csr.vals + (size_t)b * a.csr.cap;
+
+    for (int k = tid; k < n; k += PF_NT) v[k] = 1.0f;
+    if (tid == 0) cached_rows_s = 0;
+    if (ok)
+        for (int k = tid; k <= r1 - r0; k += PF_NT) rp[k] = a.csr.rowptr[(size_t)b * (n + 1) + r0 + k];
+    __syncthreads();
+    uint32_t s0 = 0;
+    if (ok) {
+        s0 = rp[0];
+        for (int k = tid + 1; k <= r1 - r0; k += PF_NT)
+            if (rp[k] - s0 <= (uint32_t)a.cache_cap) atomicMax(&cached_rows_s, k);
+    }
+    __syncthreads();
+    const int cached_rows = cached_rows_s;                     // rows [r0, r0 + cached_rows) live in shared memory
+    if (ok) {
+        const uint32_t cnt = rp[cached_rows] - s0;
+        for (uint32_t k = tid; k < cnt; k += PF_NT) {
+            cvals[k] = __ldg(gvals + s0 + k);
+            ccols[k] = __ldg(gcols + s0 + k);
+        }
+    }
+    cluster_sync_all();                                         // every CTA of the cluster is resident before remote stores
+
+    const int q = lane & 7, grp = lane >> 3;
+    uint32_t u_remote;                                          // shared::cluster address of ubuf in CTA q
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(u_remote) : "r"((uint32_t)__cvta_generic_to_shared(ubuf)), "r"(q));
+    for (int t = 1; t <= a.num_iterations; ++t) {
+        const int cur = t & 1;
+        for (int lb = warp * 4; lb < r1 - r0; lb += (PF_NT / 32) * 4) {          // warp-uniform trip count (full-mask shuffles)
+            const int li = lb + grp, i = r0 + li;
+            const bool live = li < r1 - r0;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            if (!live) {
+            } else if (ok) {
+                const uint32_t s = rp[li], e = rp[li + 1];
+                if (li < cached_rows) {
+                    for (uint32_t p = s - s0 + q, pe = e - s0; p < pe; p += 32) {
+                        a0 = __fmaf_rn(cvals[p], v[ccols[p]], a0);
+                        if (p + 8 < pe) a1 = __fmaf_rn(cvals[p + 8], v[ccols[p + 8]], a1);
+                        if (p + 16 < pe) a2 = __fmaf_rn(cvals[p + 16], v[ccols[p + 16]], a2);
+                        if (p + 24 < pe) a3 = __fmaf_rn(cvals[p + 24], v[ccols[p + 24]], a3);
+                    }
+                } else {
+                    for (uint32_t p = s + q; p < e; p += 32) {
+                        a0 = __fmaf_rn(__ldg(gvals + p), v[__ldg(gcols + p)], a0);
+                        if (p + 8 < e) a1 = __fmaf_rn(__ldg(gvals + p + 8), v[__ldg(gcols + p + 8)], a1);
+                        if (p + 16 < e) a2 = __fmaf_rn(__ldg(gvals + p + 16), v[__ldg(gcols + p + 16)], a2);
+                        if (p + 24 < e) a3 = __fmaf_rn(__ldg(gvals + p + 24), v[__ldg(gcols + p + 24)], a3);
+                    }
+                }
+            } else {
+                const Pt me = load_pt(P + i);
+                const uint32_t* row = hard + (size_t)i * a.W;
+                a0 = pf_bits_lane(P, row, me, a.W, a.d_sq, q, v);
+                a1 = pf_bits_lane(P, row, me, a.W, a.d_sq, q + 8, v);
+                a2 = pf_bits_lane(P, row, me, a.W, a.d_sq, q + 16, v);
+                a3 = pf_bits_lane(P, row, me, a.W, a.d_sq, q + 24, v);
+            }
+            float acc = __fadd_rn(__fadd_rn(a0, a2), __fadd_rn(a1, a3));       // butterfly offsets 16, 8
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            if (live) asm volatile("st.shared::cluster.f32 [%0], %1;" :: "r"(u_remote + ((uint32_t)cur * a.n_pad + (uint32_t)i) * 4u), "f"(acc) : "memory");
+        }
+        __syncwarp();
+        cluster_sync_all();
+        const float* u = ubuf + (size_t)cur * a.n_pad;
+        if (tid < 256) {
+            double ss = 0.0;
+            for (int k = tid; k < n; k += 256) {
+                const float x = u[k];
+                ss += (double)x * (double)x;
+            }
+            ss = warp_sum_d(ss);
+            if (lane == 0) red[warp] = ss;
+        }
+        __syncthreads();
+        double tot = 0.0;
+        for (int k = 0; k < 8; ++k) tot += red[k];
+        const float denom = __fadd_rn((float)sqrt(tot), 1e-6f);
+        int notclose = 0;
+        for (int k = tid; k < n; k += PF_NT) {
+            const float x = __fdiv_rn(u[k], denom);
+            const float vp = v[k];
+            const float allowed = __fadd_rn(1e-8f, fabsf(__fmul_rn(1e-5f, vp)));
+            if (!(fabsf(__fsub_rn(x, vp)) <= allowed)) notclose = 1;
+            v[k] = x;
+        }
+        const int nc = __syncthreads_or(notclose);
+        if (nc == 0 || t == a.num_iterations) {
+            for (int k = r0 + tid; k < r1; k += PF_NT) a.conf[(size_t)b * n + k] = v[k];
+            if (rank == 0 && tid == 0) { a.iters[b] = t; a.done[b] = 1; }
+            break;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------- pick_seeds
 // SC2_PCR.py:47-51: i survives iff for all j: score_i >= score_j or ||s_i - s_j|| >= R.  The neighbourhood test is the
 // `near` bit row written by first_order_bits_kernel, so this is a sparse scan: warp per row, grid (ceil(n / 8), batch).
@@ -1352,9 +1524,20 @@ extern "C" int eyoc_sc2pcr(const float* src, const float* tgt, int batch, int n,
             EYOC_LAUNCH_CHECK();
             csr_fill_kernel<<<dim3((n + 7) / 8, batch), 256, 0, stream>>>(P, hard, n, W, cfg->d_thre_sq, csr);
             EYOC_LAUNCH_CHECK();
-            for (int t = 1; t <= I; ++t) {
-                power_step_kernel<<<dim3((n + 7) / 8, batch), 256, 0, stream>>>(P, hard, n, W, cfg->d_thre_sq, t, I, vbuf, u, conf, st, csr);
+            const int rows_per = (n + PF_C - 1) / PF_C, n_pad = (n + 3) & ~3;
+            const size_t pf_fixed = (size_t)3 * n_pad * 4 + (size_t)((rows_per + 1 + 3) & ~3) * 4;
+            if (g_power_fused && pf_fixed + 6 * 1024 <= (size_t)PF_SMEM_MAX - 256) {
+                const int cache_cap = (int)(((size_t)PF_SMEM_MAX - 256 - pf_fixed) / 6) & ~7;
+                const size_t smem = pf_fixed + (size_t)cache_cap * 6;
+                PfArgs pa{P, hard, n, W, cfg->d_thre_sq, I, conf, done, global_iters, csr, rows_per, n_pad, cache_cap};
+                EYOC_CUDA(cudaFuncSetAttribute(power_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                power_fused_kernel<<<dim3(PF_C, batch), PF_NT, smem, stream>>>(pa);
                 EYOC_LAUNCH_CHECK();
+            } else {
+                for (int t = 1; t <= I; ++t) {
+                    power_step_kernel<<<dim3((n + 7) / 8, batch), 256, 0, stream>>>(P, hard, n, W, cfg->d_thre_sq, t, I, vbuf, u, conf, st, csr);
+                    EYOC_LAUNCH_CHECK();
+                }
             }
         }
         const int32_t* seeds_use = seeds;
@@ -1545,5 +1728,10 @@ extern "C" int eyoc_power_iteration_dense(const float* M, int batch, int n, int 
         EYOC_LAUNCH_CHECK();
     }
     if (iters_out) EYOC_CUDA(cudaMemcpyAsync(iters_out, iters, sizeof(int), cudaMemcpyDeviceToDevice, stream));
+    return EYOC_OK;
+}
+
+extern "C" int eyoc_debug_sc2_power_fused(int on) {
+    g_power_fused = on ? 1 : 0;
     return EYOC_OK;
 }

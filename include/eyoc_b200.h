@@ -236,6 +236,10 @@ int eyoc_sparse_conv_h(const void* in0, int c0, const void* in1, int c1, const i
                        float acc_scale, const float* scale, const float* shift, const void* residual, int residual_packed,
                        int relu, int l2norm, void* out, int out_packed, int cout, int32_t* range_status, uint32_t* counters,
                        eyoc_stream_t stream);
+/* Test aid of eyoc_sc2pcr: 1 (default) = the leading-eigenvector power iteration of a pair runs in one launch on a cluster of
+ * 8 CTAs; 0 = one launch per iteration (the path taken anyway when n is too large for the cluster's shared memory).  Both
+ * return the same bits. */
+int eyoc_debug_sc2_power_fused(int on);
 /* Test aid: cap gridDim.x of the persistent grid (0 = one CTA per SM), so that small inputs walk many tile pairs per CTA. */
 int eyoc_debug_convh_grid_cap(int max_ctas);
 /* Tuning aid: 1 = one MMA-issuing thread in the 128-channel instantiation (default), 2 = one per accumulator tile. */

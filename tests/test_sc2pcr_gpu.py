@@ -220,3 +220,35 @@ def test_vs_torch_cuda_reference(golden_dir, name):
     untied = counts[np.searchsorted(vals, sc[theirs])] == 1             # this score occurs once in the whole pair
     assert untied.mean() > 0.3 and np.array_equal(mine[untied], theirs[untied])
     assert np.array_equal(np.sort(sc[mine])[::-1], sc[theirs])          # the same score multiset, descending
+
+
+@pytest.mark.parametrize('n,inlier_frac,batch', [(5, 1.0, 2), (700, 1.0, 2), (1003, 0.3, 3), (4000, 0.02, 2), (8000, 0.15, 3)])
+def test_power_iteration_cluster_kernel_matches_stepwise(n, inlier_frac, batch):
+    """The one-launch power iteration (a cluster of 8 CTAs per pair, iterate in shared memory, u exchanged through distributed
+    shared memory) returns the bits of the launch-per-iteration kernel: confidence, stopping iteration and everything after.
+    Covers n < cluster size, n not a multiple of 8, a pair too dense for the CSR image (all inliers at n = 700: the
+    recompute-from-coordinates rows) and the benchmark's size."""
+    from eyoc_b200 import _C
+    from eyoc_b200.scripts.SC2_PCR.SC2_PCR import Matcher
+    rng = np.random.default_rng(n)
+    src = rng.uniform(-40, 40, (batch, n, 3)).astype(np.float32)
+    ang = 0.3
+    R = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]], np.float32)
+    tgt = src @ R.T + np.float32([1.0, -2.0, 0.5]) + rng.normal(0, 0.02, src.shape).astype(np.float32)
+    out = rng.random((batch, n)) >= inlier_frac
+    tgt[out] = rng.uniform(-40, 40, (int(out.sum()), 3)).astype(np.float32)
+    s, t = torch.from_numpy(src).cuda(), torch.from_numpy(tgt).cuda()
+    m = Matcher(inlier_threshold=0.6, num_node='all', use_mutual=False, d_thre=0.1, num_iterations=20, ratio=0.2,
+                nms_radius=0.6, max_points=8000, k1=30, k2=20)
+    res = {}
+    try:
+        for fused in (0, 1):
+            assert _C.lib().eyoc_debug_sc2_power_fused(fused) == 0
+            det = {}
+            T, fit, labels = m._run(s, t, want_labels=True, detail=det)
+            res[fused] = (det['confidence'].clone(), det['global_iters'].clone(), det['seeds'].clone(), T.clone(), labels.clone())
+    finally:
+        _C.lib().eyoc_debug_sc2_power_fused(1)
+    assert bool(torch.isfinite(res[1][0]).all()) and float(res[1][0].abs().max()) > 0
+    for a, b in zip(res[0], res[1]):
+        assert torch.equal(a, b)
