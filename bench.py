@@ -262,16 +262,22 @@ def run_ours(args):
 
     e2e_phase = {}
 
+    small_e2e = args.e2e_diag == 'noupload'
+
     def run_e2e(n_steps):
         ticket, pl = feeder.get()
         pending, last = None, None
         acc = [0.0] * 4
+        marks = [torch.cuda.Event(enable_timing=True)]
+        marks[0].record()
         for k in range(n_steps):
             t0_ = time.perf_counter()
             t = ticket.wait()
             plan_k = dict(pl, fc0=t['fc0'], fc1=t['fc1'], src=t['src'], tgt=t['tgt'], fc_uniform=True)
-            out = pipe.run(t['coords'], t['xyz'], sizes, plan=plan_k, descriptors=desc_d)
+            out = pipe.run(coords_d if small_e2e else t['coords'], xyz_d if small_e2e else t['xyz'], sizes, plan=plan_k, descriptors=desc_d)
             ticket.release()                                       # its buffers may be refilled a few blocks from now
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
             t1_ = time.perf_counter()
             ar = AsyncRecords(pipe.records(out, ids_dev), P * world, host_out=rec_hosts[k & 1])
             t2_ = time.perf_counter()
@@ -283,7 +289,10 @@ def run_ours(args):
             t4_ = time.perf_counter()
             for i_, d_ in enumerate((t1_ - t0_, t2_ - t1_, t3_ - t2_, t4_ - t3_)):
                 acc[i_] += d_
+        t5_ = time.perf_counter()
         last = pending.result()
+        e2e_phase.update(drain_ms=1e3 * (time.perf_counter() - t5_),
+                         gpu_block_ms=[round(a.elapsed_time(b), 2) for a, b in zip(marks[:-1], marks[1:])])
         e2e_phase.update(host_ms_per_step={'pipe_run_launch': 1e3 * acc[0] / n_steps, 'records_async': 1e3 * acc[1] / n_steps,
                                            'wait_for_feeder': 1e3 * acc[2] / n_steps, 'wait_prev_records': 1e3 * acc[3] / n_steps})
         return last
@@ -330,8 +339,21 @@ def run_ours(args):
     # ---- end-to-end timing through the public API with host inputs
     # the feeder thread plans (fresh host RNG draws), stages and uploads block i + 1 .. i + 2 while block i computes
     sys.setswitchinterval(2e-4)            # two Python threads (feeder, launcher): hand the GIL over quickly
-    feeder = BlockFeeder(pipe, (dict(coords=coords_h, xyz=xyz_h, sizes=sizes) for _ in range(K + 8)), dev, depth=2)
-    run_e2e(2)
+    feed_pipe = pipe
+    if args.e2e_diag == 'noplan':
+        class _CachedPlan:
+            def __init__(self, pl):
+                self.pl = pl
+
+            def plan(self, sizes_):
+                return self.pl
+        feed_pipe = _CachedPlan(pipe.plan(sizes))
+    small = args.e2e_diag == 'noupload'
+    feeder = BlockFeeder(feed_pipe, (dict(coords=coords_h[:8] if small else coords_h, xyz=xyz_h[:8] if small else xyz_h, sizes=sizes)
+                                     for _ in range(K + 12)), dev, depth=K + 4 if args.e2e_diag == 'prefetch' else 2)
+    run_e2e(6)                             # every slot of the uploader has its pinned / device buffers before the timed loop
+    if args.e2e_diag == 'prefetch':
+        time.sleep(3.0)
     barrier()
     t0 = time.perf_counter()
     rec_e2e = run_e2e(K)
@@ -436,7 +458,9 @@ def run_ours(args):
                        'value_mode': 'coordinates, points and index plans resident in HBM', 'conv_mode': enn.CONV_MODE, 'tile_order': bool(enn.TILE_ORDER)},
             'e2e': {'value': e2e, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(h2d_bytes),
                     'd2h_bytes_per_step': int(rec_hosts[0].numel() * 4), 'ms_per_step': 1e3 * e2e_s / K,
-                    'host_phases': e2e_phase.get('host_ms_per_step'),
+                    'host_phases': e2e_phase.get('host_ms_per_step'), 'drain_ms': e2e_phase.get('drain_ms'),
+                    'gpu_block_ms': e2e_phase.get('gpu_block_ms'),
+                    **({'diag': args.e2e_diag} if args.e2e_diag else {}),
                     'overlap': 'a feeder thread plans (host RNG), stages and uploads block i+1 on a copy stream; all-gather + D2H of block i on side streams, read by the host one block later'},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'features_checked': features_checked,
             'gather_checked': gather_checked,
@@ -473,6 +497,8 @@ def main():
     ap.add_argument('--no-check-gather', action='store_true',
                     help='skip the world > 1 self-check (rank 0 recomputes every rank\'s block and compares the gathered table byte for byte)')
     ap.add_argument('--conv-breakdown', action='store_true')
+    ap.add_argument('--e2e-diag', default=None, choices=['prefetch', 'noplan', 'noupload'],
+                    help='diagnostic only (the e2e figure is then NOT an end-to-end number): prefetch = every block planned and uploaded before the timed loop')
     ap.add_argument('--no-tile-order', action='store_true')
     ap.add_argument('--wide-issuers', type=int, default=0, help='tuning: MMA-issuing threads of the 128-channel conv instantiation')
     ap.add_argument('--tile-group-mb', type=float, default=None, help='L2 budget of one cloud group of the tile order (sparse.TILE_GROUP_BYTES)')

@@ -10,6 +10,7 @@
 // All of it is integer work bounded by HBM/L2 latency; lookups are one probe sequence per (k, o) with
 // coalesced writes along o.
 #include "common.cuh"
+#include "xh_format.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include "../../include/eyoc_b200.h"
 
@@ -373,6 +374,177 @@ __global__ void permute_columns_kernel(const int* __restrict__ nbr, int n_out, c
     out[k * n_out + i] = __ldg(nbr + k * n_out + __ldg(perm + i));
 }
 
+// ------------------------------------------------------------------------------------------------- stem convolution
+// The network's first layer (model/resunet.py:31-37: conv1, 1 -> 32 channels, 5^3 offsets, stride 1) without a 125-column
+// neighbour table.  Probing the coordinate hash for all 124 offsets is ~85 % misses on surface-like clouds, so an
+// OCCUPANCY table is built first: one 64-bit mask per 4x4x4 block of voxels (bit = x&3 | (y&3)<<2 | (z&3)<<4).  A KS^3
+// neighbourhood (KS <= 5) spans at most 2x2x2 blocks, so a row reads eight masks (shared with its neighbours through L1),
+// extracts the KS occupancy bits of every (dy, dz) line with two shifts, and probes the coordinate hash only where a
+// voxel exists (every such probe hits).  The convolution accumulates in ascending k exactly like sparse_conv_cin1_kernel,
+// the BN affine / ReLU epilogue and the split-half packing are applied in registers, and the 3^3 sub-cube of the
+// neighbourhood leaves as the level's 3^3 neighbour table (identical to eyoc_kernel_map_self's).
+__global__ void block_clear_kernel(ulonglong2* __restrict__ slots, long long cap) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) slots[i] = make_ulonglong2(EMPTY, 0ull);
+}
+
+__global__ void block_insert_kernel(const int* __restrict__ coords, int n, ulonglong2* slots, long long cap) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int4 c = make_int4(0, 0, 0, 0);
+    bool valid = i < n;
+    if (valid) {
+        c = reinterpret_cast<const int4*>(coords)[i];
+        valid = c.x >= 0 && c.x <= 65535 && in_range16(c.y) && in_range16(c.z) && in_range16(c.w);
+    }
+    const unsigned active = __ballot_sync(0xffffffffu, valid);
+    if (!valid) return;
+    const unsigned long long key = pack4(c.x, c.y >> 2, c.z >> 2, c.w >> 2);
+    const int bit = (c.y & 3) | ((c.z & 3) << 2) | ((c.w & 3) << 4);
+    // rows of one warp that fall into the same block (neighbours in scan / sort order usually do) insert once
+    const unsigned peers = __match_any_sync(active, key);
+    const unsigned lo = __reduce_or_sync(peers, bit < 32 ? 1u << bit : 0u);
+    const unsigned hi = __reduce_or_sync(peers, bit >= 32 ? 1u << (bit - 32) : 0u);
+    if ((int)(threadIdx.x & 31) != __ffs(peers) - 1) return;
+    const unsigned long long mask = ((unsigned long long)hi << 32) | lo;
+    long long slot = (long long)(mix64(key) & (unsigned long long)(cap - 1));
+    while (true) {
+        const unsigned long long prev = atomicCAS(&slots[slot].x, EMPTY, key);
+        if (prev == EMPTY || prev == key) {
+            atomicOr(&slots[slot].y, mask);
+            return;
+        }
+        slot = (slot + 1) & (cap - 1);
+    }
+}
+
+struct StemArgs {
+    const int* coords;
+    int n;
+    const unsigned long long* keys;
+    const int* vals;
+    long long cap;
+    const ulonglong2* blocks;
+    long long bcap;
+    const float* in;        // [n] the single input channel
+    const float* weight;    // [KS^3, 32]
+    const float* scale;
+    const float* shift;
+    int relu;
+    float* out;             // [n, 32] fp32, or
+    uint8_t* out_xh;        // [n] split-half rows of 32 channels (128 bytes)
+    int* range_status;
+    int* nbr3;              // [27, n] or null
+};
+
+template <int KS>
+__global__ void __launch_bounds__(128)
+stem_conv_kernel(const StemArgs a) {
+    constexpr int K3 = KS * KS * KS, r = (KS - 1) / 2, CO = 32;
+    extern __shared__ float stem_w[];                         // [K3][32]
+    __shared__ unsigned long long ms[8][128];                 // the 2x2x2 block masks of each thread's row
+    const int tid = threadIdx.x;
+    for (int e = tid; e < K3 * CO; e += 128) stem_w[e] = a.weight[e];
+    __syncthreads();
+    const int o = blockIdx.x * 128 + tid;
+    if (o >= a.n) return;
+    const int4 c = reinterpret_cast<const int4*>(a.coords)[o];
+    const int bx0 = (c.y - r) >> 2, by0 = (c.z - r) >> 2, bz0 = (c.w - r) >> 2;
+    const int bx1 = (c.y + r) >> 2, by1 = (c.z + r) >> 2, bz1 = (c.w + r) >> 2;
+    {
+        unsigned long long bkey[8];
+        ulonglong2 got[8];
+        long long bslot[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            bkey[j] = pack4(c.x, (j & 1) ? bx1 : bx0, (j & 2) ? by1 : by0, (j & 4) ? bz1 : bz0);
+            bslot[j] = (long long)(mix64(bkey[j]) & (unsigned long long)(a.bcap - 1));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) got[j] = __ldg(a.blocks + bslot[j]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            unsigned long long m = 0ull;
+            if (got[j].x == bkey[j]) m = got[j].y;
+            else if (got[j].x != EMPTY) {
+                long long sl = (bslot[j] + 1) & (a.bcap - 1);
+                while (true) {
+                    const ulonglong2 g2 = __ldg(a.blocks + sl);
+                    if (g2.x == bkey[j]) { m = g2.y; break; }
+                    if (g2.x == EMPTY) break;
+                    sl = (sl + 1) & (a.bcap - 1);
+                }
+            }
+            ms[j][tid] = m;
+        }
+    }
+    float acc[CO];
+#pragma unroll
+    for (int ch = 0; ch < CO; ++ch) acc[ch] = 0.f;
+    const int sx = (c.y - r) & 3;                              // x offset of the window inside block bx0
+#pragma unroll 1
+    for (int g = 0; g < KS * KS; ++g) {
+        const int iy = g % KS - r, iz = g / KS - r;
+        const int yy = c.z + iy, zz = c.w + iz;
+        const int jy = (yy >> 2) - by0, jz = (zz >> 2) - bz0;                   // 0 or 1
+        const int pos = ((yy & 3) << 2) | ((zz & 3) << 4);
+        const unsigned long long m0 = ms[jz * 4 + jy * 2][tid], m1 = ms[jz * 4 + jy * 2 + 1][tid];
+        const unsigned line = (unsigned)((m0 >> pos) & 0xFull) | ((unsigned)((m1 >> pos) & 0xFull) << 4);   // 8 voxels along x
+        unsigned bits = (line >> sx) & ((1u << KS) - 1u);
+        const bool centre = g == (KS * KS) / 2;
+        if (centre) bits &= ~(1u << r);                                           // the row itself needs no probe
+        unsigned long long key[KS];
+        bool act[KS];
+        int v[KS];
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+            act[j] = (bits >> j) & 1u;
+            key[j] = pack4(c.x, c.y + j - r, yy, zz);
+        }
+        hash_lookup_row<KS>(a.keys, a.vals, a.cap, key, act, v);
+        if (centre) v[r] = o;
+        float x[KS];
+#pragma unroll
+        for (int j = 0; j < KS; ++j) x[j] = v[j] >= 0 ? __ldg(a.in + v[j]) : 0.f;
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+            if (v[j] < 0) continue;
+            const float4* w4 = reinterpret_cast<const float4*>(stem_w + (g * KS + j) * CO);
+#pragma unroll
+            for (int q = 0; q < CO / 4; ++q) {
+                const float4 w = w4[q];
+                acc[4 * q + 0] = __fmaf_rn(x[j], w.x, acc[4 * q + 0]);
+                acc[4 * q + 1] = __fmaf_rn(x[j], w.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = __fmaf_rn(x[j], w.z, acc[4 * q + 2]);
+                acc[4 * q + 3] = __fmaf_rn(x[j], w.w, acc[4 * q + 3]);
+            }
+        }
+        if (a.nbr3 && iy >= -1 && iy <= 1 && iz >= -1 && iz <= 1) {
+#pragma unroll
+            for (int j3 = 0; j3 < 3; ++j3)
+                a.nbr3[(size_t)(j3 + 3 * (iy + 1) + 9 * (iz + 1)) * a.n + o] = v[r - 1 + j3];
+        }
+    }
+    bool bad = false;
+#pragma unroll
+    for (int ch = 0; ch < CO; ++ch) {
+        float y = acc[ch];
+        if (a.scale) y = __fmaf_rn(y, __ldg(a.scale + ch), a.shift ? __ldg(a.shift + ch) : 0.f);
+        else if (a.shift) y += __ldg(a.shift + ch);
+        if (a.relu) y = fmaxf(y, 0.f);
+        bad |= !(fabsf(y) < 65504.f);
+        acc[ch] = y;
+    }
+    if (a.out_xh) {
+        if (bad && a.range_status) atomicOr(a.range_status, 1);
+#pragma unroll
+        for (int col = 0; col < CO; col += 8) xh_store8(a.out_xh + (size_t)o * CO * 4, col, acc + col);
+    } else {
+#pragma unroll
+        for (int ch = 0; ch < CO; ch += 4)
+            *reinterpret_cast<float4*>(a.out + (size_t)o * CO + ch) = make_float4(acc[ch], acc[ch + 1], acc[ch + 2], acc[ch + 3]);
+    }
+}
+
 }  // namespace
 
 extern "C" size_t eyoc_tile_order_workspace_bytes(int64_t n_out) {
@@ -566,6 +738,36 @@ extern "C" int eyoc_parity_class(const int32_t* coords, int64_t n, int ts, int32
     EYOC_CHECK_ARG(coords && cls && ts >= 1, "eyoc_parity_class: bad argument");
     if (n == 0) return EYOC_OK;
     parity_class_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(coords, (int)n, ts, cls);
+    EYOC_LAUNCH_CHECK();
+    return EYOC_OK;
+}
+
+extern "C" size_t eyoc_stem_conv_workspace_bytes(int64_t capacity) { return (size_t)capacity * 16 + 256; }
+
+extern "C" int eyoc_stem_conv(const int32_t* coords, int64_t n, const uint64_t* table_keys, const int32_t* table_vals, int64_t capacity,
+                              int ksize, const float* in, const float* weight, const float* scale, const float* shift, int relu,
+                              void* out, int out_packed, int32_t* range_status, int32_t* nbr3, void* workspace,
+                              size_t workspace_bytes, cudaStream_t stream) {
+    EYOC_CHECK_ARG(coords && table_keys && table_vals && in && weight && out, "eyoc_stem_conv: null argument");
+    EYOC_CHECK_ARG(ksize == 3 || ksize == 5, "eyoc_stem_conv: kernel size must be 3 or 5 (got %d)", ksize);
+    EYOC_CHECK_ARG(n >= 0 && n < (1ll << 31), "eyoc_stem_conv: bad n");
+    EYOC_CHECK_ARG(capacity >= 2 * n && capacity >= 2 && (capacity & (capacity - 1)) == 0, "eyoc_stem_conv: capacity must be a power of two >= 2n");
+    if (n == 0) return EYOC_OK;
+    if (workspace == nullptr || workspace_bytes < eyoc_stem_conv_workspace_bytes(capacity)) {
+        eyoc_set_error("eyoc_stem_conv: workspace too small");
+        return EYOC_ERR_WORKSPACE;
+    }
+    ulonglong2* blocks = (ulonglong2*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    block_clear_kernel<<<(unsigned)((capacity + 255) / 256), 256, 0, stream>>>(blocks, capacity);
+    EYOC_LAUNCH_CHECK();
+    block_insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(coords, (int)n, blocks, capacity);
+    EYOC_LAUNCH_CHECK();
+    StemArgs a{coords, (int)n, (const unsigned long long*)table_keys, table_vals, capacity, blocks, capacity, in, weight, scale, shift,
+               relu, out_packed ? nullptr : (float*)out, out_packed ? (uint8_t*)out : nullptr, range_status, nbr3};
+    const size_t smem = (size_t)ksize * ksize * ksize * 32 * sizeof(float);
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    if (ksize == 3) stem_conv_kernel<3><<<grid, 128, smem, stream>>>(a);
+    else stem_conv_kernel<5><<<grid, 128, smem, stream>>>(a);
     EYOC_LAUNCH_CHECK();
     return EYOC_OK;
 }

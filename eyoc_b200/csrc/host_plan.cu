@@ -204,6 +204,10 @@ extern "C" int eyoc_plan_draws(uint32_t* mt_key624, int32_t* mt_pos, int num_pai
     };
     unsigned nthreads = std::thread::hardware_concurrency();
     nthreads = nthreads < 1 ? 1 : (nthreads > 8 ? 8 : nthreads);
+    if (const char* e = getenv("EYOC_PLAN_THREADS")) {          // tuning: worker threads of the replay pass (1..64)
+        const int v = atoi(e);
+        if (v >= 1 && v <= 64) nthreads = (unsigned)v;
+    }
     if ((int)nthreads > num_pairs) nthreads = num_pairs > 0 ? (unsigned)num_pairs : 1u;
     std::atomic<int> next(0);
     auto loop = [&]() { for (int p = next.fetch_add(1); p < num_pairs; p = next.fetch_add(1)) work(p); };

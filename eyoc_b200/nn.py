@@ -124,6 +124,8 @@ class MinkowskiBatchNorm(nn.Module):
 CONV_MODE = 'f16x3'
 # Tensor-core convolutions tile their output rows in (cloud group, neighbour pattern) order (CoordinateManager.tiled_map)
 TILE_ORDER = True
+# The 1-channel first convolution runs fused with its neighbour search (CoordinateManager.stem_conv)
+STEM_FUSED = True
 
 
 def split_weights(weight):
@@ -259,6 +261,23 @@ def conv_bn_act(x, conv, norm=None, residual=None, relu=False, l2norm=False, ski
     K = conv.kernel_size ** 3
     use_h = h_supported(c0_, c1_, conv.out_channels, K, l2norm)
     use_tc = use_h or tc_supported(c0_, c1_, conv.out_channels, K, l2norm)
+    if (STEM_FUSED and c0_ == 1 and skip is None and residual is None and not l2norm and conv.out_channels == 32
+            and conv.kernel_size in (3, 5) and ts_in == 1 and ts_out == 1 and not conv.TRANSPOSED and mgr.num_rows(1) > 0):
+        scale = shift = None
+        if norm is not None:
+            scale, shift = norm.folded()
+            if conv.bias is not None:
+                shift = shift + conv.bias.view(-1) * scale
+        elif conv.bias is not None:
+            shift = conv.bias.view(-1)
+        feats = x.F.reshape(-1).contiguous()
+        _C.require_cuda(feats, conv.kernel, scale, shift)
+        packed = CONV_MODE == 'f16x3'
+        out = mgr.stem_conv(feats, conv.kernel.detach().contiguous(), scale, shift, relu, conv.kernel_size, packed)
+        key = CoordinateMapKey(1)
+        if packed:
+            return SparseTensor(features_xh=out, coordinate_map_key=key, coordinate_manager=mgr)
+        return SparseTensor(out, coordinate_map_key=key, coordinate_manager=mgr)
     nbr = None
     row_perm = None
     masks = None

@@ -205,6 +205,25 @@ class CoordinateManager:
             self._maps[key] = nbr
         return self._maps[key]
 
+    def stem_conv(self, feats, weight, scale, shift, relu, ksize, packed):
+        """The network's first convolution (1 input channel -> 32, 3^3 or 5^3 offsets, stride 1 on the stride-1 map) fused with
+        its own neighbour search (eyoc_stem_conv: block-occupancy pre-filter, no ksize^3-column table).  Returns the output rows
+        (split-half fp16 when ``packed``) and leaves the level's 3^3 neighbour table in the map cache as a by-product."""
+        lv = self.levels[1]
+        lib = _C.lib()
+        out = torch.empty((lv.n, 64) if packed else (lv.n, 32), dtype=torch.float16 if packed else torch.float32, device=self.device)
+        key3 = (1, 1, 3, False)
+        nbr3 = torch.empty((27, lv.n), dtype=torch.int32, device=self.device) if key3 not in self._maps else None
+        ws = torch.empty(lib.eyoc_stem_conv_workspace_bytes(_C.c_int64(lv.cap)), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _C.check(lib.eyoc_stem_conv(_C.ptr(lv.coords), _C.c_int64(lv.n), _C.ptr(lv.keys), _C.ptr(lv.vals), _C.c_int64(lv.cap),
+                                        _C.c_int(ksize), _C.ptr(feats), _C.ptr(weight), _C.ptr(scale), _C.ptr(shift),
+                                        _C.c_int(int(relu)), _C.ptr(out), _C.c_int(int(packed)), _C.ptr(self.range_status),
+                                        _C.ptr(nbr3), _C.ptr(ws), _C.c_size_t(ws.numel()), _C.stream()))
+        if nbr3 is not None:
+            self._maps[key3] = nbr3
+        return out
+
     def tiled_map(self, ts_in, ts_out, ksize, transposed=False):
         """(nbr_tiled [K, N_out], row_perm [N_out]) for the tensor-core convolution: output rows sorted by
         (cloud group, neighbour-pattern bit mask) so that 128-row tiles are dense or skipped per kernel offset

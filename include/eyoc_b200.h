@@ -207,6 +207,19 @@ int eyoc_sparse_conv_tc(const float* in0, int c0, const float* in1, int c1, cons
                         const float* shift, const float* residual, int relu, int l2norm, float* out, int cout,
                         eyoc_stream_t stream);
 
+/* The network's first convolution (reference model/resunet.py:31-37 `conv1`: ME.MinkowskiConvolution(1, 32, kernel_size=5,
+ * stride=1) + model/resunet.py:38 `norm1` + ReLU of :147-150) fused with its own neighbour search on the stride-1 coordinate
+ * set: `in` [n] is the single input channel, `weight` [ksize^3, 32] (k = ix + ks (iy + ks iz), as eyoc_kernel_map), ksize 3 or 5;
+ * coords / table_* / capacity are eyoc_hash_build's.  out: [n, 32] fp32 rows, or split-half rows (128 bytes) when out_packed
+ * (range_status as eyoc_xh_pack).  nbr3 (optional) [27, n] receives the 3^3 neighbour table of the same coordinate set,
+ * identical to eyoc_kernel_map_self(ksize = 3).  Same accumulation order (k ascending) and epilogue as eyoc_sparse_conv with
+ * the full table.  workspace: eyoc_stem_conv_workspace_bytes(capacity) (an occupancy table, one 64-bit mask per 4x4x4 block). */
+size_t eyoc_stem_conv_workspace_bytes(int64_t capacity);
+int eyoc_stem_conv(const int32_t* coords, int64_t n, const uint64_t* table_keys, const int32_t* table_vals, int64_t capacity,
+                   int ksize, const float* in, const float* weight, const float* scale, const float* shift, int relu, void* out,
+                   int out_packed, int32_t* range_status, int32_t* nbr3, void* workspace, size_t workspace_bytes,
+                   eyoc_stream_t stream);
+
 /* fp16 hi/lo split data path of the same operator (csrc/sparse_conv_h.cu): tcgen05.mma kind::f16, activations kept in
  * HBM in the SPLIT-HALF format - a row of c channels (c % 32 == 0) is c / 32 chunks of 128 bytes, each 32 fp16 "hi"
  * values followed by 32 fp16 "lo'" values with x = hi + lo' * 2^-11 (|x| < 65504; 22 significant bits, 4 c bytes per
