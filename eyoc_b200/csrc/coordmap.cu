@@ -367,11 +367,22 @@ __global__ void tile_key_remap_kernel(unsigned long long* __restrict__ keys, int
     keys[o] = (key & ~0x7ffffffull) | r;
 }
 
-__global__ void permute_columns_kernel(const int* __restrict__ nbr, int n_out, const int* __restrict__ perm, int* __restrict__ out) {
+// nbr_tiled[k, i] = nbr[k, perm[i]]: grid (tiles of 256 rows, K).  The tile's "offset k has a neighbour" bit - what
+// eyoc_tile_masks computes from the tiled table afterwards - is one block-wide OR of values already in registers.
+__global__ void __launch_bounds__(256)
+permute_columns_kernel(const int* __restrict__ nbr, int n_out, const int* __restrict__ perm, int* __restrict__ out,
+                       unsigned int* __restrict__ masks) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_out) return;
     const size_t k = blockIdx.y;
-    out[k * n_out + i] = __ldg(nbr + k * n_out + __ldg(perm + i));
+    int v = -1;
+    if (i < n_out) {
+        v = __ldg(nbr + k * n_out + __ldg(perm + i));
+        out[k * n_out + i] = v;
+    }
+    if (masks) {
+        const int any = __syncthreads_or(v >= 0);
+        if (threadIdx.x == 0 && any) atomicOr(masks + blockIdx.x, 1u << blockIdx.y);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------- stem convolution
@@ -425,7 +436,7 @@ struct StemArgs {
     long long cap;
     const ulonglong2* blocks;
     long long bcap;
-    const float* in;        // [n] the single input channel
+    const float* in;        // [n] the single input channel; null = every value is 1.0
     const float* weight;    // [KS^3, 32]
     const float* scale;
     const float* shift;
@@ -436,21 +447,49 @@ struct StemArgs {
     int* nbr3;              // [27, n] or null
 };
 
+// One warp per 32 rows, 8 warps per CTA.
+//   A (lane = row): the 2x2x2 block masks -> the row's KS^3-bit occupancy.
+//   B: the set bits of the warp's rows become one list of (row, k) entries, rows in order, k ascending within a row.
+//   C (lane = entry, 4 entries per lane in flight): hash probe (always a hit) -> neighbour row -> its input value; entries of
+//      the 3^3 sub-cube also go to the warp's [27][32] slice of the neighbour table.
+//   D (half-warp = row, lane = 2 output channels): each row's entries are accumulated in list order (= k ascending, the order
+//      of sparse_conv_cin1_kernel), then BN affine / ReLU / store (fp32 row, or the split-half row: 64 B of hi, 64 B of lo').
+// Only neighbours that exist cost instructions: ~18 of 124 on LiDAR surfaces, where a thread-per-row loop over all offsets
+// pays for every offset that ANY of its warp's 32 rows has.
+constexpr int STEM_NT = 256;
+constexpr int STEM_ECAP = 960;          // list entries per pass (a row has <= 125: at least 7 rows per pass)
+constexpr int STEM_WARP_BYTES = STEM_ECAP * 8 + 27 * 32 * 4 + 32 * 16 + 36 * 4;
+
 template <int KS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(STEM_NT)
 stem_conv_kernel(const StemArgs a) {
-    constexpr int K3 = KS * KS * KS, r = (KS - 1) / 2, CO = 32;
-    extern __shared__ float stem_w[];                         // [K3][32]
-    __shared__ unsigned long long ms[8][128];                 // the 2x2x2 block masks of each thread's row
-    const int tid = threadIdx.x;
-    for (int e = tid; e < K3 * CO; e += 128) stem_w[e] = a.weight[e];
+    constexpr int K3 = KS * KS * KS, r = (KS - 1) / 2, CO = 32, CENTRE = K3 / 2;
+    static_assert(K3 <= 128, "entry encoding: 7 bits of k");
+    extern __shared__ __align__(16) unsigned char stem_smem[];
+    float* w_s = reinterpret_cast<float*>(stem_smem);                               // [K3][32]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char* mine = stem_smem + (size_t)K3 * CO * 4 + (size_t)warp * STEM_WARP_BYTES;
+    uint2* rec = reinterpret_cast<uint2*>(mine);                                     // [ECAP] B: (., row << 7 | k)  C: (x, k * 32)
+    unsigned long long* ms = reinterpret_cast<unsigned long long*>(mine);            // [8][32] block masks (phase A only)
+    int* n3 = reinterpret_cast<int*>(mine + STEM_ECAP * 8);                          // [27][32]
+    int4* cs = reinterpret_cast<int4*>(mine + STEM_ECAP * 8 + 27 * 32 * 4);          // [32] coordinates of the warp's rows
+    int* roff = reinterpret_cast<int*>(mine + STEM_ECAP * 8 + 27 * 32 * 4 + 32 * 16);    // [33] entry offsets of the rows
+    for (int e = tid; e < K3 * CO; e += STEM_NT) w_s[e] = a.weight[e];
     __syncthreads();
-    const int o = blockIdx.x * 128 + tid;
-    if (o >= a.n) return;
-    const int4 c = reinterpret_cast<const int4*>(a.coords)[o];
-    const int bx0 = (c.y - r) >> 2, by0 = (c.z - r) >> 2, bz0 = (c.w - r) >> 2;
-    const int bx1 = (c.y + r) >> 2, by1 = (c.z + r) >> 2, bz1 = (c.w + r) >> 2;
-    {
+    const int o_base = (blockIdx.x * (STEM_NT / 32) + warp) * 32;
+    if (o_base >= a.n) return;                                   // whole warp out of range (no CTA barrier below)
+    const int o = o_base + lane;
+    const bool valid = o < a.n;
+    // ---------------------------------------------------------------- A: occupancy of the row's neighbourhood
+    unsigned long long occ_lo = 0ull, occ_hi = 0ull;
+    int4 c = make_int4(0, 0, 0, 0);
+    if (valid) c = reinterpret_cast<const int4*>(a.coords)[o];
+    cs[lane] = c;
+#pragma unroll
+    for (int k3 = 0; k3 < 27; ++k3) n3[k3 * 32 + lane] = -1;
+    if (valid) {
+        const int bx0 = (c.y - r) >> 2, by0 = (c.z - r) >> 2, bz0 = (c.w - r) >> 2;
+        const int bx1 = (c.y + r) >> 2, by1 = (c.z + r) >> 2, bz1 = (c.w + r) >> 2;
         unsigned long long bkey[8];
         ulonglong2 got[8];
         long long bslot[8];
@@ -474,74 +513,141 @@ stem_conv_kernel(const StemArgs a) {
                     sl = (sl + 1) & (a.bcap - 1);
                 }
             }
-            ms[j][tid] = m;
+            ms[j * 32 + lane] = m;
         }
-    }
-    float acc[CO];
+        const int sx = (c.y - r) & 3;                              // x offset of the window inside block bx0
 #pragma unroll
-    for (int ch = 0; ch < CO; ++ch) acc[ch] = 0.f;
-    const int sx = (c.y - r) & 3;                              // x offset of the window inside block bx0
-#pragma unroll 1
-    for (int g = 0; g < KS * KS; ++g) {
-        const int iy = g % KS - r, iz = g / KS - r;
-        const int yy = c.z + iy, zz = c.w + iz;
-        const int jy = (yy >> 2) - by0, jz = (zz >> 2) - bz0;                   // 0 or 1
-        const int pos = ((yy & 3) << 2) | ((zz & 3) << 4);
-        const unsigned long long m0 = ms[jz * 4 + jy * 2][tid], m1 = ms[jz * 4 + jy * 2 + 1][tid];
-        const unsigned line = (unsigned)((m0 >> pos) & 0xFull) | ((unsigned)((m1 >> pos) & 0xFull) << 4);   // 8 voxels along x
-        unsigned bits = (line >> sx) & ((1u << KS) - 1u);
-        const bool centre = g == (KS * KS) / 2;
-        if (centre) bits &= ~(1u << r);                                           // the row itself needs no probe
-        unsigned long long key[KS];
-        bool act[KS];
-        int v[KS];
-#pragma unroll
-        for (int j = 0; j < KS; ++j) {
-            act[j] = (bits >> j) & 1u;
-            key[j] = pack4(c.x, c.y + j - r, yy, zz);
-        }
-        hash_lookup_row<KS>(a.keys, a.vals, a.cap, key, act, v);
-        if (centre) v[r] = o;
-        float x[KS];
-#pragma unroll
-        for (int j = 0; j < KS; ++j) x[j] = v[j] >= 0 ? __ldg(a.in + v[j]) : 0.f;
-#pragma unroll
-        for (int j = 0; j < KS; ++j) {
-            if (v[j] < 0) continue;
-            const float4* w4 = reinterpret_cast<const float4*>(stem_w + (g * KS + j) * CO);
-#pragma unroll
-            for (int q = 0; q < CO / 4; ++q) {
-                const float4 w = w4[q];
-                acc[4 * q + 0] = __fmaf_rn(x[j], w.x, acc[4 * q + 0]);
-                acc[4 * q + 1] = __fmaf_rn(x[j], w.y, acc[4 * q + 1]);
-                acc[4 * q + 2] = __fmaf_rn(x[j], w.z, acc[4 * q + 2]);
-                acc[4 * q + 3] = __fmaf_rn(x[j], w.w, acc[4 * q + 3]);
+        for (int g = 0; g < KS * KS; ++g) {
+            const int iy = g % KS - r, iz = g / KS - r;
+            const int yy = c.z + iy, zz = c.w + iz;
+            const int jy = (yy >> 2) - by0, jz = (zz >> 2) - bz0;                   // 0 or 1
+            const int pos = ((yy & 3) << 2) | ((zz & 3) << 4);
+            const unsigned long long m0 = ms[(jz * 4 + jy * 2) * 32 + lane], m1 = ms[(jz * 4 + jy * 2 + 1) * 32 + lane];
+            const unsigned line = (unsigned)((m0 >> pos) & 0xFull) | ((unsigned)((m1 >> pos) & 0xFull) << 4);   // 8 voxels along x
+            const unsigned long long bits = (line >> sx) & ((1u << KS) - 1u);
+            const int bp = g * KS;                                 // compile-time after unrolling
+            if (bp < 64) {
+                occ_lo |= bits << bp;
+                if (bp + KS > 64) occ_hi |= bits >> (64 - bp);
+            } else {
+                occ_hi |= bits << (bp - 64);
             }
         }
-        if (a.nbr3 && iy >= -1 && iy <= 1 && iz >= -1 && iz <= 1) {
-#pragma unroll
-            for (int j3 = 0; j3 < 3; ++j3)
-                a.nbr3[(size_t)(j3 + 3 * (iy + 1) + 9 * (iz + 1)) * a.n + o] = v[r - 1 + j3];
-        }
     }
+    __syncwarp();                                                  // ms (aliased by rec) is dead from here on
+    // ---------------------------------------------------------------- B..D in passes of <= STEM_ECAP entries
+    const int cnt = __popcll(occ_lo) + __popcll(occ_hi);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += y;
+    }
+    const int half = lane >> 4, l2 = (lane & 15) * 2;              // phase D: half-warp = row, lane = channels l2, l2 + 1
+    const float sc0 = a.scale ? __ldg(a.scale + l2) : 1.f, sc1 = a.scale ? __ldg(a.scale + l2 + 1) : 1.f;
+    const float sh0 = a.shift ? __ldg(a.shift + l2) : 0.f, sh1 = a.shift ? __ldg(a.shift + l2 + 1) : 0.f;
     bool bad = false;
+    int r_begin = 0;
+    while (r_begin < 32) {
+        const int base = r_begin ? __shfl_sync(0xffffffffu, incl, r_begin - 1) : 0;
+        const unsigned fits = __ballot_sync(0xffffffffu, incl - base <= STEM_ECAP);
+        const int r_end = 32 - __clz(fits);                        // incl is monotone: rows [r_begin, r_end) fit (r_end > r_begin)
+        const int n_ent = __shfl_sync(0xffffffffu, incl, r_end - 1) - base;
+        if (lane >= r_begin && lane < r_end) {
+            int e = incl - cnt - base;
+            roff[lane] = e;
+            unsigned long long m = occ_lo;
+            while (m) { const int k = __ffsll((long long)m) - 1; m &= m - 1; rec[e++].y = (unsigned)((lane << 7) | k); }
+            m = occ_hi;
+            while (m) { const int k = 64 + __ffsll((long long)m) - 1; m &= m - 1; rec[e++].y = (unsigned)((lane << 7) | k); }
+        }
+        if (lane == 0) roff[r_end] = n_ent;
+        __syncwarp();
+        // C: probes
+        for (int e0 = 0; e0 < n_ent; e0 += 128) {
+            unsigned long long key[4];
+            bool act[4];
+            int v[4], kk[4], rr[4];
 #pragma unroll
-    for (int ch = 0; ch < CO; ++ch) {
-        float y = acc[ch];
-        if (a.scale) y = __fmaf_rn(y, __ldg(a.scale + ch), a.shift ? __ldg(a.shift + ch) : 0.f);
-        else if (a.shift) y += __ldg(a.shift + ch);
-        if (a.relu) y = fmaxf(y, 0.f);
-        bad |= !(fabsf(y) < 65504.f);
-        acc[ch] = y;
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * 32 + lane;
+                const unsigned en = e < n_ent ? rec[e].y : 0u;
+                kk[u] = en & 127;
+                rr[u] = en >> 7;
+                const int4 cc = cs[rr[u]];
+                const int ix = kk[u] % KS - r, iy = (kk[u] / KS) % KS - r, iz = kk[u] / (KS * KS) - r;
+                // with an all-ones input only the 3^3 sub-cube (the neighbour table) needs the neighbour's row
+                const bool need_row = a.in != nullptr || (a.nbr3 && ix >= -1 && ix <= 1 && iy >= -1 && iy <= 1 && iz >= -1 && iz <= 1);
+                act[u] = e < n_ent && kk[u] != CENTRE && need_row;
+                key[u] = pack4(cc.x, cc.y + ix, cc.z + iy, cc.w + iz);
+            }
+            hash_lookup_row<4>(a.keys, a.vals, a.cap, key, act, v);
+            float x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (kk[u] == CENTRE) v[u] = o_base + rr[u];
+                x[u] = 1.0f;
+                if (a.in) x[u] = (e0 + u * 32 + lane < n_ent && v[u] >= 0) ? __ldg(a.in + v[u]) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * 32 + lane;
+                if (e < n_ent) {
+                    rec[e] = make_uint2(__float_as_uint(x[u]), (unsigned)(kk[u] * CO));
+                    const int ix = kk[u] % KS - r, iy = (kk[u] / KS) % KS - r, iz = kk[u] / (KS * KS) - r;
+                    if (ix >= -1 && ix <= 1 && iy >= -1 && iy <= 1 && iz >= -1 && iz <= 1)
+                        n3[((ix + 1) + 3 * (iy + 1) + 9 * (iz + 1)) * 32 + rr[u]] = v[u];
+                }
+            }
+        }
+        __syncwarp();
+        // D: two rows at a time, one per half-warp
+        for (int rw0 = r_begin; rw0 < r_end; rw0 += 2) {
+            const int rw = rw0 + half;
+            const int orow = o_base + rw;
+            const bool live = rw < r_end && orow < a.n;
+            int e = live ? roff[rw] : 0;
+            const int e1 = live ? roff[rw + 1] : 0;
+            float acc0 = 0.f, acc1 = 0.f;
+            for (; e + 4 <= e1; e += 4) {
+                const uint2 q0 = rec[e], q1 = rec[e + 1], q2 = rec[e + 2], q3 = rec[e + 3];
+                const float2 w0 = *reinterpret_cast<const float2*>(w_s + q0.y + l2), w1 = *reinterpret_cast<const float2*>(w_s + q1.y + l2);
+                const float2 w2 = *reinterpret_cast<const float2*>(w_s + q2.y + l2), w3 = *reinterpret_cast<const float2*>(w_s + q3.y + l2);
+                acc0 = __fmaf_rn(__uint_as_float(q0.x), w0.x, acc0); acc1 = __fmaf_rn(__uint_as_float(q0.x), w0.y, acc1);
+                acc0 = __fmaf_rn(__uint_as_float(q1.x), w1.x, acc0); acc1 = __fmaf_rn(__uint_as_float(q1.x), w1.y, acc1);
+                acc0 = __fmaf_rn(__uint_as_float(q2.x), w2.x, acc0); acc1 = __fmaf_rn(__uint_as_float(q2.x), w2.y, acc1);
+                acc0 = __fmaf_rn(__uint_as_float(q3.x), w3.x, acc0); acc1 = __fmaf_rn(__uint_as_float(q3.x), w3.y, acc1);
+            }
+            for (; e < e1; ++e) {
+                const uint2 q0 = rec[e];
+                const float2 w0 = *reinterpret_cast<const float2*>(w_s + q0.y + l2);
+                acc0 = __fmaf_rn(__uint_as_float(q0.x), w0.x, acc0); acc1 = __fmaf_rn(__uint_as_float(q0.x), w0.y, acc1);
+            }
+            if (live) {
+                float y0 = acc0, y1 = acc1;
+                if (a.scale) { y0 = __fmaf_rn(y0, sc0, sh0); y1 = __fmaf_rn(y1, sc1, sh1); }
+                else if (a.shift) { y0 += sh0; y1 += sh1; }
+                if (a.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+                bad |= !(fabsf(y0) < 65504.f) || !(fabsf(y1) < 65504.f);
+                if (a.out_xh) {
+                    __half h0, g0, h1, g1;
+                    xh_split(y0, h0, g0);
+                    xh_split(y1, h1, g1);
+                    __half2* row = reinterpret_cast<__half2*>(a.out_xh + (size_t)orow * CO * 4);
+                    row[lane & 15] = __halves2half2(h0, h1);
+                    row[16 + (lane & 15)] = __halves2half2(g0, g1);
+                } else {
+                    *reinterpret_cast<float2*>(a.out + (size_t)orow * CO + l2) = make_float2(y0, y1);
+                }
+            }
+        }
+        __syncwarp();
+        r_begin = r_end;
     }
-    if (a.out_xh) {
-        if (bad && a.range_status) atomicOr(a.range_status, 1);
+    if (a.out_xh && a.range_status && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(a.range_status, 1);
+    if (a.nbr3 && valid) {
 #pragma unroll
-        for (int col = 0; col < CO; col += 8) xh_store8(a.out_xh + (size_t)o * CO * 4, col, acc + col);
-    } else {
-#pragma unroll
-        for (int ch = 0; ch < CO; ch += 4)
-            *reinterpret_cast<float4*>(a.out + (size_t)o * CO + ch) = make_float4(acc[ch], acc[ch + 1], acc[ch + 2], acc[ch + 3]);
+        for (int k3 = 0; k3 < 27; ++k3) a.nbr3[(size_t)k3 * a.n + o] = n3[k3 * 32 + lane];
     }
 }
 
@@ -555,7 +661,8 @@ extern "C" size_t eyoc_tile_order_workspace_bytes(int64_t n_out) {
 }
 
 extern "C" int eyoc_tile_order(const int32_t* nbr, int K, int64_t n_out, const int32_t* out_coords, int group_clouds, int max_batch,
-                               int32_t* row_perm, int32_t* nbr_tiled, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                               int32_t* row_perm, int32_t* nbr_tiled, uint32_t* tile_masks, void* workspace, size_t workspace_bytes,
+                               cudaStream_t stream) {
     EYOC_CHECK_ARG(nbr && out_coords && row_perm && nbr_tiled, "eyoc_tile_order: null argument");
     EYOC_CHECK_ARG(K >= 1 && K <= 27 && group_clouds >= 1 && max_batch >= 0 && max_batch <= 65535, "eyoc_tile_order: bad K / group / batch");
     EYOC_CHECK_ARG(n_out >= 0 && n_out < (1ll << 31), "eyoc_tile_order: bad n_out");
@@ -585,7 +692,8 @@ extern "C" int eyoc_tile_order(const int32_t* nbr, int K, int64_t n_out, const i
     while ((max_batch / group_clouds) >> gbits) ++gbits;
     EYOC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, temp, keys, keys2, iota, row_perm, (int)n_out, 0, 27 + gbits, stream));
     g_eyoc_launches += 4;
-    permute_columns_kernel<<<dim3(g, K), 256, 0, stream>>>(nbr, (int)n_out, row_perm, nbr_tiled);
+    if (tile_masks) EYOC_CUDA(cudaMemsetAsync(tile_masks, 0, (size_t)g * sizeof(uint32_t), stream));
+    permute_columns_kernel<<<dim3(g, K), 256, 0, stream>>>(nbr, (int)n_out, row_perm, nbr_tiled, tile_masks);
     EYOC_LAUNCH_CHECK();
     return EYOC_OK;
 }
@@ -748,7 +856,7 @@ extern "C" int eyoc_stem_conv(const int32_t* coords, int64_t n, const uint64_t* 
                               int ksize, const float* in, const float* weight, const float* scale, const float* shift, int relu,
                               void* out, int out_packed, int32_t* range_status, int32_t* nbr3, void* workspace,
                               size_t workspace_bytes, cudaStream_t stream) {
-    EYOC_CHECK_ARG(coords && table_keys && table_vals && in && weight && out, "eyoc_stem_conv: null argument");
+    EYOC_CHECK_ARG(coords && table_keys && table_vals && weight && out, "eyoc_stem_conv: null argument");
     EYOC_CHECK_ARG(ksize == 3 || ksize == 5, "eyoc_stem_conv: kernel size must be 3 or 5 (got %d)", ksize);
     EYOC_CHECK_ARG(n >= 0 && n < (1ll << 31), "eyoc_stem_conv: bad n");
     EYOC_CHECK_ARG(capacity >= 2 * n && capacity >= 2 && (capacity & (capacity - 1)) == 0, "eyoc_stem_conv: capacity must be a power of two >= 2n");
@@ -764,10 +872,15 @@ extern "C" int eyoc_stem_conv(const int32_t* coords, int64_t n, const uint64_t* 
     EYOC_LAUNCH_CHECK();
     StemArgs a{coords, (int)n, (const unsigned long long*)table_keys, table_vals, capacity, blocks, capacity, in, weight, scale, shift,
                relu, out_packed ? nullptr : (float*)out, out_packed ? (uint8_t*)out : nullptr, range_status, nbr3};
-    const size_t smem = (size_t)ksize * ksize * ksize * 32 * sizeof(float);
-    const unsigned grid = (unsigned)((n + 127) / 128);
-    if (ksize == 3) stem_conv_kernel<3><<<grid, 128, smem, stream>>>(a);
-    else stem_conv_kernel<5><<<grid, 128, smem, stream>>>(a);
+    const size_t smem = (size_t)ksize * ksize * ksize * 32 * sizeof(float) + (size_t)(STEM_NT / 32) * STEM_WARP_BYTES;
+    const unsigned grid = (unsigned)((n + STEM_NT - 1) / STEM_NT);
+    if (ksize == 3) {
+        EYOC_CUDA(cudaFuncSetAttribute(stem_conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stem_conv_kernel<3><<<grid, STEM_NT, smem, stream>>>(a);
+    } else {
+        EYOC_CUDA(cudaFuncSetAttribute(stem_conv_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stem_conv_kernel<5><<<grid, STEM_NT, smem, stream>>>(a);
+    }
     EYOC_LAUNCH_CHECK();
     return EYOC_OK;
 }

@@ -270,7 +270,7 @@ def conv_bn_act(x, conv, norm=None, residual=None, relu=False, l2norm=False, ski
                 shift = shift + conv.bias.view(-1) * scale
         elif conv.bias is not None:
             shift = conv.bias.view(-1)
-        feats = x.F.reshape(-1).contiguous()
+        feats = None if x.all_ones else x.F.reshape(-1).contiguous()      # None: every input value is 1.0 (sparse.ones_features)
         _C.require_cuda(feats, conv.kernel, scale, shift)
         packed = CONV_MODE == 'f16x3'
         out = mgr.stem_conv(feats, conv.kernel.detach().contiguous(), scale, shift, relu, conv.kernel_size, packed)

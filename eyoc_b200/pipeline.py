@@ -13,7 +13,7 @@ import torch
 
 from . import _C
 from .lib.eval import knn1
-from .sparse import SparseTensor
+from .sparse import SparseTensor, ones_features
 
 RECORD_FLOATS = 24     # T (16) | n_inliers | best_seed | pair_id | status | nn_hit_ratio | 3 pad
 
@@ -140,7 +140,7 @@ class RegistrationPipeline:
             return a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
 
         P = len(sizes)
-        feats_in = torch.ones((coords.shape[0], 1), dtype=torch.float32, device=dev)
+        feats_in = ones_features(coords.shape[0], dev)            # lib/data_loaders.py:971-972: occupancy-only input
         F = self.model(SparseTensor(feats_in, coordinates=coords)).F
         Fm = F if descriptors is None else descriptors
         out = {'features': F}

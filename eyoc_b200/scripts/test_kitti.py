@@ -123,7 +123,7 @@ class RawPairLoader:
         return len(self.pairs)
 
     def __iter__(self):
-        from ..sparse import voxelize_gpu
+        from ..sparse import ones_features, voxelize_gpu
         for xyz0, xyz1, T in self.pairs:
             out = {}
             for i, xyz in enumerate((xyz0, xyz1)):
@@ -131,7 +131,7 @@ class RawPairLoader:
                 coords, sel = voxelize_gpu(x, self.voxel_size)
                 out[f'pcd{i}'] = [x[sel].cpu()]
                 out[f'sinput{i}_C'] = coords
-                out[f'sinput{i}_F'] = torch.ones((coords.shape[0], 1), device=self.device)
+                out[f'sinput{i}_F'] = ones_features(coords.shape[0], self.device)
             out['T_gt'] = [torch.as_tensor(T, dtype=torch.float32)]
             yield out
 

@@ -239,13 +239,16 @@ class CoordinateManager:
             group = max(1, min(self.max_batch + 1, int(TILE_GROUP_BYTES // (rows_per_cloud * 4 * cin_hint))))
             perm = torch.empty(n_out, dtype=torch.int32, device=self.device)
             tiled = torch.empty_like(nbr)
+            masks = torch.empty(max(1, (n_out + 255) // 256), dtype=torch.int32, device=self.device)
             lib = _C.lib()
             ws = torch.empty(max(lib.eyoc_tile_order_workspace_bytes(_C.c_int64(n_out)), 8), dtype=torch.uint8, device=self.device)
             with torch.cuda.device(self.device):
                 _C.check(lib.eyoc_tile_order(_C.ptr(nbr), _C.c_int(K), _C.c_int64(n_out), _C.ptr(lout.coords), _C.c_int(group),
-                                             _C.c_int(self.max_batch), _C.ptr(perm), _C.ptr(tiled), _C.ptr(ws),
+                                             _C.c_int(self.max_batch), _C.ptr(perm), _C.ptr(tiled), _C.ptr(masks), _C.ptr(ws),
                                              _C.c_size_t(ws.numel()), _C.stream()))
             self._tiled[key] = (tiled, perm)
+            if n_out > 0:
+                self._tile_masks[key] = masks         # per 256-row tile, out of the same pass (else eyoc_tile_masks)
         return self._tiled[key]
 
     def tile_masks(self, ts_in, ts_out, ksize, transposed=False):
@@ -294,6 +297,15 @@ def xh_unpack(xh):
     return out
 
 
+def ones_features(n, device):
+    """The reference's network input - ``torch.ones((N, 1))`` occupancy features (lib/data_loaders.py:971-972) - tagged so that
+    the first convolution knows every value is 1.0 and does not gather it (eyoc_stem_conv with ``in`` = NULL).  Do not write
+    to the returned tensor."""
+    t = torch.ones((n, 1), dtype=torch.float32, device=device)
+    t._eyoc_all_ones = True
+    return t
+
+
 class SparseTensor:
     """Features [N, C] fp32 on a coordinate set; row order == input order (the reference relies on it).
 
@@ -319,6 +331,7 @@ class SparseTensor:
             coordinate_map_key = CoordinateMapKey(tensor_stride)
         self._F = features
         self._Fh = features_xh
+        self.all_ones = bool(getattr(features, '_eyoc_all_ones', False))       # see ones_features()
         self.coordinate_manager = coordinate_manager
         self.coordinate_map_key = coordinate_map_key
         n = coordinate_manager.levels[coordinate_map_key.tensor_stride].coords.shape[0]

@@ -166,10 +166,12 @@ int eyoc_kernel_map_transpose(const int32_t* nbr_down, int64_t n_coarse, int64_t
  * of the kernel offsets that have a neighbour - the offsets ordered by how many rows have them, the rarest in the most
  * significant bit, ties by offset index), nbr_tiled[k, i] = nbr[k, row_perm[i]].  Rows with the same neighbour
  * pattern share 128-row tiles (dense or skipped (tile, offset) items) while each group of clouds stays contiguous
- * (L2 working set of the gather).  K <= 27; max_batch = largest batch index (sizes the sort key). */
+ * (L2 working set of the gather).  K <= 27; max_batch = largest batch index (sizes the sort key).  tile_masks (optional,
+ * [ceil(n_out / 256)]) receives what eyoc_tile_masks computes from nbr_tiled, out of the same pass. */
 size_t eyoc_tile_order_workspace_bytes(int64_t n_out);
 int eyoc_tile_order(const int32_t* nbr, int K, int64_t n_out, const int32_t* out_coords, int group_clouds, int max_batch,
-                    int32_t* row_perm, int32_t* nbr_tiled, void* workspace, size_t workspace_bytes, eyoc_stream_t stream);
+                    int32_t* row_perm, int32_t* nbr_tiled, uint32_t* tile_masks, void* workspace, size_t workspace_bytes,
+                    eyoc_stream_t stream);
 /* cls[i] = parity class (3 bits) of coords[i] / ts: groups the rows of a transposed stride-2 convolution by
  * their set of admissible kernel offsets. */
 int eyoc_parity_class(const int32_t* coords, int64_t n, int ts, int32_t* cls, eyoc_stream_t stream);
@@ -209,7 +211,8 @@ int eyoc_sparse_conv_tc(const float* in0, int c0, const float* in1, int c1, cons
 
 /* The network's first convolution (reference model/resunet.py:31-37 `conv1`: ME.MinkowskiConvolution(1, 32, kernel_size=5,
  * stride=1) + model/resunet.py:38 `norm1` + ReLU of :147-150) fused with its own neighbour search on the stride-1 coordinate
- * set: `in` [n] is the single input channel, `weight` [ksize^3, 32] (k = ix + ks (iy + ks iz), as eyoc_kernel_map), ksize 3 or 5;
+ * set: `in` [n] is the single input channel (NULL = every value is 1.0, the occupancy-only input the reference feeds:
+ * lib/data_loaders.py / scripts/test_kitti.py build `feats = ones(N, 1)`; only the 27 offsets of nbr3 are then probed), `weight` [ksize^3, 32] (k = ix + ks (iy + ks iz), as eyoc_kernel_map), ksize 3 or 5;
  * coords / table_* / capacity are eyoc_hash_build's.  out: [n, 32] fp32 rows, or split-half rows (128 bytes) when out_packed
  * (range_status as eyoc_xh_pack).  nbr3 (optional) [27, n] receives the 3^3 neighbour table of the same coordinate set,
  * identical to eyoc_kernel_map_self(ksize = 3).  Same accumulation order (k ascending) and epilogue as eyoc_sparse_conv with

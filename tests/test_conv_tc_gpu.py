@@ -120,6 +120,15 @@ def test_tile_order_and_tiled_conv():
     assert mgr.max_batch == 5 and 1 <= group < 6
     assert torch.equal(torch.sort(perm.long())[0], torch.arange(n, device='cuda'))
     assert torch.equal(tiled, nbr[:, perm.long()])
+    # the per-tile offset masks that come out of the same pass == eyoc_tile_masks on the tiled table == a torch restatement
+    from eyoc_b200 import _C
+    m_pass = mgr.tile_masks(1, 1, 3)
+    m_ref = torch.empty_like(m_pass)
+    _C.check(_C.lib().eyoc_tile_masks(_C.ptr(tiled), _C.c_int(27), _C.c_int64(n), _C.ptr(m_ref), _C.stream()))
+    pad = (-n) % 256
+    present = torch.nn.functional.pad((tiled >= 0), (0, pad)).view(27, -1, 256).any(2).long()          # [27, tiles]
+    m_torch = sum(present[k] << k for k in range(27)).to(torch.int32)
+    assert torch.equal(m_pass, m_ref) and torch.equal(m_pass, m_torch)
     # sort key: (cloud group, neighbour mask with the offsets ordered by frequency - the rarest offset in the top bit,
     # ties by offset index)
     bits = (nbr >= 0).long()                                       # [27, n]

@@ -70,3 +70,25 @@ def test_stem_conv_matches_table_path(kind, ksize, mode):
         assert a[0].dtype == b[0].dtype and torch.equal(a[0], b[0])
         assert torch.equal(a[1], b[1])
     assert float(res[True, False][0].float().abs().max()) > 0
+
+
+@pytest.mark.parametrize('kind', ['lidar', 'edges'])
+@pytest.mark.parametrize('ksize', [5, 3])
+def test_stem_conv_all_ones_input(kind, ksize):
+    """sparse.ones_features (the reference's occupancy-only input, lib/data_loaders.py:971-972) lets the kernel skip the gather
+    of the input value and every probe outside the 3^3 sub-cube: same rows, same neighbour table as a plain ones tensor."""
+    from eyoc_b200 import nn as enn
+    from eyoc_b200.sparse import SparseTensor, ones_features
+    rng = np.random.default_rng(3)
+    coords = torch.from_numpy(_coords(kind, rng)).cuda()
+    conv = enn.MinkowskiConvolution(1, 32, kernel_size=ksize, stride=1, dimension=3).cuda()
+    with torch.no_grad():
+        conv.kernel.copy_(torch.from_numpy(rng.normal(size=tuple(conv.kernel.shape)).astype(np.float32)))
+    res = []
+    for feats in (torch.ones((len(coords), 1), device='cuda'), ones_features(len(coords), 'cuda')):
+        x = SparseTensor(feats, coordinates=coords)
+        assert x.all_ones == (len(res) == 1)
+        with torch.no_grad():
+            y = enn.conv_bn_act(x, conv, None, relu=True)
+        res.append((y.Fh.clone(), x.coordinate_manager.kernel_map(1, 1, 3).clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])

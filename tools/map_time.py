@@ -27,7 +27,16 @@ def main():
         print(f'--- pass {rep}')
         mgr = timed('hash build (level 1)', lambda: CoordinateManager(coords))
         timed('levels 2, 4, 8', lambda: mgr.ensure_levels(8))
+        w = torch.randn(125, 32, device=dev)
+        ones = torch.ones(coords.shape[0], device=dev)
+        for packed in (False, True):
+            mgr._maps.pop((1, 1, 3, False), None)
+            timed(f'stem conv k5 (+ k3 table) packed={packed}', lambda: mgr.stem_conv(ones, w, None, None, True, 5, packed))
+        mgr._maps.pop((1, 1, 3, False), None)
+        timed('stem conv k5 (+ k3 table) all-ones input', lambda: mgr.stem_conv(None, w, None, None, True, 5, True))
+        mgr._maps.pop((1, 1, 3, False), None)
         timed('map k5 s1 (self)', lambda: mgr.kernel_map(1, 1, 5))
+        mgr._maps.pop((1, 1, 5, False), None)
         for ts in (1, 2, 4, 8):
             timed(f'map k3 ts{ts} (self)', lambda: mgr.kernel_map(ts, ts, 3))
         for ts in (1, 2, 4):
