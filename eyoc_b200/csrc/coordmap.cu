@@ -447,6 +447,59 @@ struct StemArgs {
     int* nbr3;              // [27, n] or null
 };
 
+// Phase A of the stem kernels: the 2x2x2 block masks around the row (staged in ms[8][32], one column per lane) -> the
+// KS^3-bit occupancy of its neighbourhood, bit k = ix + KS (iy + KS iz) in (occ_lo, occ_hi).
+template <int KS>
+__device__ __forceinline__ void stem_occupancy(const StemArgs& a, const int4 c, int lane, unsigned long long* ms,
+                                               unsigned long long& occ_lo, unsigned long long& occ_hi) {
+    constexpr int r = (KS - 1) / 2;
+    const int bx0 = (c.y - r) >> 2, by0 = (c.z - r) >> 2, bz0 = (c.w - r) >> 2;
+    const int bx1 = (c.y + r) >> 2, by1 = (c.z + r) >> 2, bz1 = (c.w + r) >> 2;
+    unsigned long long bkey[8];
+    ulonglong2 got[8];
+    long long bslot[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        bkey[j] = pack4(c.x, (j & 1) ? bx1 : bx0, (j & 2) ? by1 : by0, (j & 4) ? bz1 : bz0);
+        bslot[j] = (long long)(mix64(bkey[j]) & (unsigned long long)(a.bcap - 1));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) got[j] = __ldg(a.blocks + bslot[j]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        unsigned long long m = 0ull;
+        if (got[j].x == bkey[j]) m = got[j].y;
+        else if (got[j].x != EMPTY) {
+            long long sl = (bslot[j] + 1) & (a.bcap - 1);
+            while (true) {
+                const ulonglong2 g2 = __ldg(a.blocks + sl);
+                if (g2.x == bkey[j]) { m = g2.y; break; }
+                if (g2.x == EMPTY) break;
+                sl = (sl + 1) & (a.bcap - 1);
+            }
+        }
+        ms[j * 32 + lane] = m;
+    }
+    const int sx = (c.y - r) & 3;                              // x offset of the window inside block bx0
+#pragma unroll
+    for (int g = 0; g < KS * KS; ++g) {
+        const int iy = g % KS - r, iz = g / KS - r;
+        const int yy = c.z + iy, zz = c.w + iz;
+        const int jy = (yy >> 2) - by0, jz = (zz >> 2) - bz0;                   // 0 or 1
+        const int pos = ((yy & 3) << 2) | ((zz & 3) << 4);
+        const unsigned long long m0 = ms[(jz * 4 + jy * 2) * 32 + lane], m1 = ms[(jz * 4 + jy * 2 + 1) * 32 + lane];
+        const unsigned line = (unsigned)((m0 >> pos) & 0xFull) | ((unsigned)((m1 >> pos) & 0xFull) << 4);   // 8 voxels along x
+        const unsigned long long bits = (line >> sx) & ((1u << KS) - 1u);
+        const int bp = g * KS;                                 // compile-time after unrolling
+        if (bp < 64) {
+            occ_lo |= bits << bp;
+            if (bp + KS > 64) occ_hi |= bits >> (64 - bp);
+        } else {
+            occ_hi |= bits << (bp - 64);
+        }
+    }
+}
+
 // One warp per 32 rows, 8 warps per CTA.
 //   A (lane = row): the 2x2x2 block masks -> the row's KS^3-bit occupancy.
 //   B: the set bits of the warp's rows become one list of (row, k) entries, rows in order, k ascending within a row.
@@ -487,53 +540,7 @@ stem_conv_kernel(const StemArgs a) {
     cs[lane] = c;
 #pragma unroll
     for (int k3 = 0; k3 < 27; ++k3) n3[k3 * 32 + lane] = -1;
-    if (valid) {
-        const int bx0 = (c.y - r) >> 2, by0 = (c.z - r) >> 2, bz0 = (c.w - r) >> 2;
-        const int bx1 = (c.y + r) >> 2, by1 = (c.z + r) >> 2, bz1 = (c.w + r) >> 2;
-        unsigned long long bkey[8];
-        ulonglong2 got[8];
-        long long bslot[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            bkey[j] = pack4(c.x, (j & 1) ? bx1 : bx0, (j & 2) ? by1 : by0, (j & 4) ? bz1 : bz0);
-            bslot[j] = (long long)(mix64(bkey[j]) & (unsigned long long)(a.bcap - 1));
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) got[j] = __ldg(a.blocks + bslot[j]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            unsigned long long m = 0ull;
-            if (got[j].x == bkey[j]) m = got[j].y;
-            else if (got[j].x != EMPTY) {
-                long long sl = (bslot[j] + 1) & (a.bcap - 1);
-                while (true) {
-                    const ulonglong2 g2 = __ldg(a.blocks + sl);
-                    if (g2.x == bkey[j]) { m = g2.y; break; }
-                    if (g2.x == EMPTY) break;
-                    sl = (sl + 1) & (a.bcap - 1);
-                }
-            }
-            ms[j * 32 + lane] = m;
-        }
-        const int sx = (c.y - r) & 3;                              // x offset of the window inside block bx0
-#pragma unroll
-        for (int g = 0; g < KS * KS; ++g) {
-            const int iy = g % KS - r, iz = g / KS - r;
-            const int yy = c.z + iy, zz = c.w + iz;
-            const int jy = (yy >> 2) - by0, jz = (zz >> 2) - bz0;                   // 0 or 1
-            const int pos = ((yy & 3) << 2) | ((zz & 3) << 4);
-            const unsigned long long m0 = ms[(jz * 4 + jy * 2) * 32 + lane], m1 = ms[(jz * 4 + jy * 2 + 1) * 32 + lane];
-            const unsigned line = (unsigned)((m0 >> pos) & 0xFull) | ((unsigned)((m1 >> pos) & 0xFull) << 4);   // 8 voxels along x
-            const unsigned long long bits = (line >> sx) & ((1u << KS) - 1u);
-            const int bp = g * KS;                                 // compile-time after unrolling
-            if (bp < 64) {
-                occ_lo |= bits << bp;
-                if (bp + KS > 64) occ_hi |= bits >> (64 - bp);
-            } else {
-                occ_hi |= bits << (bp - 64);
-            }
-        }
-    }
+    if (valid) stem_occupancy<KS>(a, c, lane, ms, occ_lo, occ_hi);
     __syncwarp();                                                  // ms (aliased by rec) is dead from here on
     // ---------------------------------------------------------------- B..D in passes of <= STEM_ECAP entries
     const int cnt = __popcll(occ_lo) + __popcll(occ_hi);
@@ -649,6 +656,109 @@ stem_conv_kernel(const StemArgs a) {
 #pragma unroll
         for (int k3 = 0; k3 < 27; ++k3) a.nbr3[(size_t)k3 * a.n + o] = n3[k3 * 32 + lane];
     }
+}
+
+// All-ones input (StemArgs.in == NULL, the reference's occupancy-only features): the convolution is a sum of the weight rows
+// of the occupied offsets, straight off the occupancy bits - no entry list, no value gather - and only the 27 offsets of the
+// 3^3 neighbour table are probed (lane = row, 9 probes in flight).  Rows are accumulated by groups of 8 lanes, four channels
+// per lane, in ascending k:  acc = fma(1.0f, w, acc)  ==  acc + w  rounded once, as in the general kernel.
+template <int KS>
+__global__ void __launch_bounds__(STEM_NT, 3)
+stem_ones_kernel(const StemArgs a) {
+    constexpr int K3 = KS * KS * KS, r = (KS - 1) / 2, CO = 32;
+    extern __shared__ __align__(16) unsigned char stem_smem[];
+    float* w_s = reinterpret_cast<float*>(stem_smem);                               // [K3][32]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned long long* ms = reinterpret_cast<unsigned long long*>(stem_smem + (size_t)K3 * CO * 4) + (size_t)warp * (8 * 32 + 64);
+    unsigned long long* occ_s = ms + 8 * 32;                                         // [32][2] occupancy of the warp's rows
+    for (int e = tid; e < K3 * CO; e += STEM_NT) w_s[e] = a.weight[e];
+    __syncthreads();
+    const int o_base = (blockIdx.x * (STEM_NT / 32) + warp) * 32;
+    if (o_base >= a.n) return;
+    const int o = o_base + lane;
+    const bool valid = o < a.n;
+    unsigned long long occ_lo = 0ull, occ_hi = 0ull;
+    int4 c = make_int4(0, 0, 0, 0);
+    if (valid) {
+        c = reinterpret_cast<const int4*>(a.coords)[o];
+        stem_occupancy<KS>(a, c, lane, ms, occ_lo, occ_hi);
+    }
+    occ_s[lane * 2] = occ_lo;
+    occ_s[lane * 2 + 1] = occ_hi;
+    // ---- the 3^3 neighbour table: z-slabs of 9 probes
+    if (a.nbr3 && valid) {
+#pragma unroll
+        for (int s3 = 0; s3 < 3; ++s3) {
+            unsigned long long key[9];
+            bool act[9];
+            int v[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                const int ix = j % 3 - 1, iy = j / 3 - 1, iz = s3 - 1;
+                const int k = (ix + r) + KS * ((iy + r) + KS * (iz + r));           // compile-time
+                const bool occ = k < 64 ? (occ_lo >> (k & 63)) & 1ull : (occ_hi >> ((k - 64) & 63)) & 1ull;
+                act[j] = occ && !(ix == 0 && iy == 0 && iz == 0);
+                key[j] = pack4(c.x, c.y + ix, c.z + iy, c.w + iz);
+            }
+            hash_lookup_row<9>(a.keys, a.vals, a.cap, key, act, v);
+            if (s3 == 1) v[4] = o;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) a.nbr3[(size_t)(s3 * 9 + j) * a.n + o] = v[j];
+        }
+    }
+    __syncwarp();
+    // ---- convolution: 8 lanes = one row (4 rows of the warp at a time), lane = channels l4 .. l4 + 3; the occupancy is walked
+    //      as 32-bit words (little endian halves of occ_lo / occ_hi), ascending k
+    const unsigned int* occ32 = reinterpret_cast<const unsigned int*>(occ_s);       // [32][4]
+    const int sub = lane >> 3, l4 = (lane & 7) * 4;
+    float sc[4], sh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        sc[j] = a.scale ? __ldg(a.scale + l4 + j) : 1.f;
+        sh[j] = a.shift ? __ldg(a.shift + l4 + j) : 0.f;
+    }
+    bool bad = false;
+    for (int rw0 = 0; rw0 < 32; rw0 += 4) {
+        const int rw = rw0 + sub, orow = o_base + rw;
+        if (orow >= a.n) continue;
+        float y[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int wd = 0; wd < (K3 + 31) / 32; ++wd) {
+            unsigned int m = occ32[rw * 4 + wd];
+            while (m) {
+                const int k = wd * 32 + __ffs((int)m) - 1;
+                m &= m - 1;
+                const float4 w = *reinterpret_cast<const float4*>(w_s + k * CO + l4);
+                y[0] = __fadd_rn(y[0], w.x);
+                y[1] = __fadd_rn(y[1], w.y);
+                y[2] = __fadd_rn(y[2], w.z);
+                y[3] = __fadd_rn(y[3], w.w);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (a.scale) y[j] = __fmaf_rn(y[j], sc[j], sh[j]);
+            else if (a.shift) y[j] += sh[j];
+            if (a.relu) y[j] = fmaxf(y[j], 0.f);
+            bad |= !(fabsf(y[j]) < 65504.f);
+        }
+        if (a.out_xh) {
+            __half h[4], g[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xh_split(y[j], h[j], g[j]);
+            uint2 hv, gv;
+            *reinterpret_cast<__half2*>(&hv.x) = __halves2half2(h[0], h[1]);
+            *reinterpret_cast<__half2*>(&hv.y) = __halves2half2(h[2], h[3]);
+            *reinterpret_cast<__half2*>(&gv.x) = __halves2half2(g[0], g[1]);
+            *reinterpret_cast<__half2*>(&gv.y) = __halves2half2(g[2], g[3]);
+            uint8_t* row = a.out_xh + (size_t)orow * CO * 4;
+            *reinterpret_cast<uint2*>(row + l4 * 2) = hv;
+            *reinterpret_cast<uint2*>(row + 64 + l4 * 2) = gv;
+        } else {
+            *reinterpret_cast<float4*>(a.out + (size_t)orow * CO + l4) = make_float4(y[0], y[1], y[2], y[3]);
+        }
+    }
+    if (a.out_xh && a.range_status && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(a.range_status, 1);
 }
 
 }  // namespace
@@ -872,14 +982,25 @@ extern "C" int eyoc_stem_conv(const int32_t* coords, int64_t n, const uint64_t* 
     EYOC_LAUNCH_CHECK();
     StemArgs a{coords, (int)n, (const unsigned long long*)table_keys, table_vals, capacity, blocks, capacity, in, weight, scale, shift,
                relu, out_packed ? nullptr : (float*)out, out_packed ? (uint8_t*)out : nullptr, range_status, nbr3};
-    const size_t smem = (size_t)ksize * ksize * ksize * 32 * sizeof(float) + (size_t)(STEM_NT / 32) * STEM_WARP_BYTES;
     const unsigned grid = (unsigned)((n + STEM_NT - 1) / STEM_NT);
-    if (ksize == 3) {
-        EYOC_CUDA(cudaFuncSetAttribute(stem_conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        stem_conv_kernel<3><<<grid, STEM_NT, smem, stream>>>(a);
+    if (in == nullptr) {
+        const size_t smem = (size_t)ksize * ksize * ksize * 32 * sizeof(float) + (size_t)(STEM_NT / 32) * (8 * 32 + 64) * 8;
+        if (ksize == 3) {
+            EYOC_CUDA(cudaFuncSetAttribute(stem_ones_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            stem_ones_kernel<3><<<grid, STEM_NT, smem, stream>>>(a);
+        } else {
+            EYOC_CUDA(cudaFuncSetAttribute(stem_ones_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            stem_ones_kernel<5><<<grid, STEM_NT, smem, stream>>>(a);
+        }
     } else {
-        EYOC_CUDA(cudaFuncSetAttribute(stem_conv_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        stem_conv_kernel<5><<<grid, STEM_NT, smem, stream>>>(a);
+        const size_t smem = (size_t)ksize * ksize * ksize * 32 * sizeof(float) + (size_t)(STEM_NT / 32) * STEM_WARP_BYTES;
+        if (ksize == 3) {
+            EYOC_CUDA(cudaFuncSetAttribute(stem_conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            stem_conv_kernel<3><<<grid, STEM_NT, smem, stream>>>(a);
+        } else {
+            EYOC_CUDA(cudaFuncSetAttribute(stem_conv_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            stem_conv_kernel<5><<<grid, STEM_NT, smem, stream>>>(a);
+        }
     }
     EYOC_LAUNCH_CHECK();
     return EYOC_OK;
