@@ -77,6 +77,7 @@ typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 
@@ -293,7 +294,10 @@ csr_scan_kernel(uint32_t* __restrict__ rowptr, int n, size_t cap, int* __restric
     if (tid == 0) ok[blockIdx.x] = (size_t)r[n] <= cap ? 1 : 0;
 }
 
-// grid (ceil(n / 8), batch): warp per row writes (column, SC value) for every set bit, in bit order
+// grid (ceil(n / 8), batch): warp per row writes (column, SC value) for every set bit, in bit order.  Two passes, so that the
+// expensive part is balanced over the lanes: (1) the set bits of the row become its column list (a lane owns a word, a warp scan
+// gives the positions), (2) the lanes stride over that list and evaluate one SC value each - instead of every lane looping
+// over the bits of its own word while the others wait.
 __global__ void __launch_bounds__(256)
 csr_fill_kernel(const Pt* __restrict__ P, const uint32_t* __restrict__ hard, int n, int W, float d_sq, Csr csr) {
     const int b = blockIdx.y, lane = threadIdx.x & 31;
@@ -303,11 +307,11 @@ csr_fill_kernel(const Pt* __restrict__ P, const uint32_t* __restrict__ hard, int
     const uint32_t* row = hard + ((size_t)b * n + i) * W;
     uint16_t* cols = csr.cols + (size_t)b * csr.cap;
     float* vals = csr.vals + (size_t)b * csr.cap;
-    uint32_t base = csr.rowptr[(size_t)b * (n + 1) + i];
-    const Pt me = load_pt(P + i);
+    const uint32_t begin = csr.rowptr[(size_t)b * (n + 1) + i], end = csr.rowptr[(size_t)b * (n + 1) + i + 1];
+    uint32_t base = begin;
     for (int w0 = 0; w0 < W; w0 += 32) {
         const int w = w0 + lane;
-        uint32_t m = w < W ? row[w] : 0u;
+        uint32_t m = w < W ? __ldg(row + w) : 0u;
         const int c = __popc(m);
         int x = c;
 #pragma unroll
@@ -319,13 +323,16 @@ csr_fill_kernel(const Pt* __restrict__ P, const uint32_t* __restrict__ hard, int
         while (m) {
             const int bit = __ffs(m) - 1;
             m &= m - 1;
-            const int j = w * 32 + bit;
-            const float cd = cross_dist(me, load_pt(P + j));
-            cols[pos] = (uint16_t)j;
-            vals[pos] = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fmul_rn(cd, cd), d_sq)), 0.f);
-            ++pos;
+            cols[pos++] = (uint16_t)(w * 32 + bit);
         }
         base += (uint32_t)__shfl_sync(0xffffffffu, x, 31);
+    }
+    __syncwarp();                                   // the warp's column list is visible to all of its lanes
+    const Pt me = load_pt(P + i);
+    for (uint32_t p = begin + lane; p < end; p += 32) {
+        const int j = cols[p];
+        const float cd = cross_dist(me, load_pt(P + j));
+        vals[p] = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fmul_rn(cd, cd), d_sq)), 0.f);
     }
 }
 
@@ -1153,29 +1160,40 @@ seed_kabsch_kernel(FitArgs a, int batch) {
 constexpr int FS = 8;
 __global__ void __launch_bounds__(256)
 seed_fitness_kernel(FitArgs a) {
-    __shared__ float T[FS][12];
+    __shared__ __align__(16) f32x2 T2[FS][12];            // every entry of the 3x4 transform twice: operands of the packed math
     __shared__ int cnt[8][FS];
     const int b = blockIdx.y, s0 = blockIdx.x * FS;
     const Pt* P = a.P + (size_t)b * a.n;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < FS * 12) {
         const int s = min(s0 + tid / 12, a.S - 1);
-        T[tid / 12][tid % 12] = a.seed_trans[((size_t)b * a.S + s) * 16 + tid % 12];
+        const float t = a.seed_trans[((size_t)b * a.S + s) * 16 + tid % 12];
+        T2[tid / 12][tid % 12] = pack2(t, t);
     }
     __syncthreads();
     int c[FS];
 #pragma unroll
     for (int k = 0; k < FS; ++k) c[k] = 0;
-    for (int j = tid; j < a.n; j += 256) {
-        const Pt p = load_pt(P + j);
+    // two points per thread and iteration in the halves of f32x2 registers (add / mul / fma .rn.f32x2 round each half exactly as
+    // the scalar instructions of apply_T do)
+    for (int j = tid; j < a.n; j += 512) {
+        const bool ok1 = j + 256 < a.n;
+        const Pt p0 = load_pt(P + j), p1 = load_pt(P + (ok1 ? j + 256 : j));
+        const f32x2 sx = pack2(p0.sx, p1.sx), sy = pack2(p0.sy, p1.sy), sz = pack2(p0.sz, p1.sz);
+        const f32x2 tx = pack2(p0.tx, p1.tx), ty = pack2(p0.ty, p1.ty), tz = pack2(p0.tz, p1.tz);
 #pragma unroll
         for (int k = 0; k < FS; ++k) {
-            float x, y, z;
-            apply_T(T[k], p.sx, p.sy, p.sz, x, y, z);
+            const f32x2* T = T2[k];
+            // R p + t as apply_T: 3-term dot (sequential FMA) then + t
+            const f32x2 x = add2(fma2(T[2], sz, fma2(T[1], sy, mul2(T[0], sx))), T[3]);
+            const f32x2 y = add2(fma2(T[6], sz, fma2(T[5], sy, mul2(T[4], sx))), T[7]);
+            const f32x2 z = add2(fma2(T[10], sz, fma2(T[9], sy, mul2(T[8], sx))), T[11]);
             // torch.norm(.) < thr  <=>  sum of squares < s0: sqrt_rn is monotonic and s0 (host: sqrt_threshold) is the
             // smallest fp32 whose correctly rounded root reaches thr - the root itself is never formed
-            const float dx = __fsub_rn(x, p.tx), dy = __fsub_rn(y, p.ty), dz = __fsub_rn(z, p.tz);
-            c[k] += !(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))) >= a.inlier_s0);
+            const f32x2 dx = sub2(x, tx), dy = sub2(y, ty), dz = sub2(z, tz);
+            float q0, q1;
+            unpack2(fma2(dz, dz, fma2(dy, dy, mul2(dx, dx))), q0, q1);
+            c[k] += (int)!(q0 >= a.inlier_s0) + (int)(ok1 && !(q1 >= a.inlier_s0));
         }
     }
 #pragma unroll
