@@ -191,7 +191,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from eyoc_b200 import _C, nn as enn, synth
-    from eyoc_b200.pipeline import (AsyncRecords, BlockFeeder, RegistrationPipeline, gather_records,
+    from eyoc_b200.pipeline import (AsyncRecords, BlockFeeder, OverlappedRunner, RegistrationPipeline, gather_records,
                                     plan_to_device)
     from eyoc_b200.scripts.SC2_PCR.SC2_PCR import Matcher
     from eyoc_b200.scripts.test_kitti import is_success, rte_rre
@@ -237,21 +237,33 @@ def run_ours(args):
     res_hosts = [torch.empty((P * world, 24), dtype=torch.float32).pin_memory() for _ in range(2)]
     res_state = {'k': 0, 'pending': None, 'table': None}
 
-    def step_resident():
-        # inputs resident in HBM.  The block's records leave through the path's one collective on NCCL's stream and are read
-        # back on a side stream; the host collects them one step later, so ranks are not coupled step by step.
-        out = pipe.run(coords_d, xyz_d, sizes, plan=plan_d, descriptors=desc_d)
-        ar = AsyncRecords(pipe.records(out, ids_dev), P * world, host_out=res_hosts[res_state['k'] & 1])
+    overlap = not args.no_overlap
+    runner = OverlappedRunner(pipe, dev) if overlap else None
+    res_state.update(queue=[], last_out=None)
+
+    def queue_records(out):
+        # the block's records leave through the path's one collective on NCCL's stream and are read back on a side stream; the
+        # host collects them one block later, so ranks are not coupled step by step
+        res_state['queue'].append(AsyncRecords(pipe.records(out, ids_dev), P * world, host_out=res_hosts[res_state['k'] & 1]))
         res_state['k'] += 1
-        if res_state['pending'] is not None:
-            res_state['table'] = res_state['pending'].result()
-        res_state['pending'] = ar
-        return out
+        res_state['last_out'] = out
+
+    def step_resident():
+        # inputs resident in HBM.  With overlap (default) the step queues stage 3 of the previous block on the match stream,
+        # then stages 1 + 2 of this block (pipeline.OverlappedRunner); the convolutions still run alone on the GPU.
+        if overlap:
+            runner.submit(coords_d, xyz_d, sizes, plan=plan_d, descriptors=desc_d, after_match=queue_records)
+        else:
+            queue_records(pipe.run(coords_d, xyz_d, sizes, plan=plan_d, descriptors=desc_d))
+        while len(res_state['queue']) > 1:
+            res_state['table'] = res_state['queue'].pop(0).result()
 
     def flush_resident():
-        if res_state['pending'] is not None:
-            res_state['table'] = res_state['pending'].result().clone()
-            res_state['pending'] = None
+        if overlap:
+            runner.flush()
+        for ar in res_state['queue']:
+            res_state['table'] = ar.result().clone()
+        res_state['queue'] = []
         return res_state['table']
 
     # End to end: host inputs every step.  The copies of block i + 1 (coordinates, points, the freshly drawn index plan) run on
@@ -266,31 +278,43 @@ def run_ours(args):
 
     def run_e2e(n_steps):
         ticket, pl = feeder.get()
-        pending, last = None, None
+        q, last = [], None
         acc = [0.0] * 4
         marks = [torch.cuda.Event(enable_timing=True)]
         marks[0].record()
+        e2e_runner = OverlappedRunner(pipe, dev) if overlap else None
+        if overlap:
+            marks[0].record(e2e_runner.main_stream)
         for k in range(n_steps):
             t0_ = time.perf_counter()
-            t = ticket.wait()
+            t = ticket.wait()                                      # the launching stream waits for the block's uploads
             plan_k = dict(pl, fc0=t['fc0'], fc1=t['fc1'], src=t['src'], tgt=t['tgt'], fc_uniform=True)
-            out = pipe.run(coords_d if small_e2e else t['coords'], xyz_d if small_e2e else t['xyz'], sizes, plan=plan_k, descriptors=desc_d)
-            ticket.release()                                       # its buffers may be refilled a few blocks from now
+            c_k, x_k = (coords_d, xyz_d) if small_e2e else (t['coords'], t['xyz'])
+
+            def after(out, ticket=ticket, k=k):
+                ticket.release()                                   # its buffers may be refilled a few blocks from now
+                q.append(AsyncRecords(pipe.records(out, ids_dev), P * world, host_out=rec_hosts[k & 1]))
+
+            if overlap:
+                e2e_runner.submit(c_k, x_k, sizes, plan=plan_k, descriptors=desc_d, before_match=ticket.wait, after_match=after)
+            else:
+                after(pipe.run(c_k, x_k, sizes, plan=plan_k, descriptors=desc_d))
             marks.append(torch.cuda.Event(enable_timing=True))
-            marks[-1].record()
+            marks[-1].record(e2e_runner.main_stream if overlap else torch.cuda.current_stream())
             t1_ = time.perf_counter()
-            ar = AsyncRecords(pipe.records(out, ids_dev), P * world, host_out=rec_hosts[k & 1])
-            t2_ = time.perf_counter()
+            t2_ = t1_
             ticket, pl = feeder.get()                              # block k + 1: planned, staged and copied by the feeder thread
             t3_ = time.perf_counter()
-            if pending is not None:
-                last = pending.result()                            # the host blocks on block k - 1's records only
-            pending = ar
+            while len(q) > 1:
+                last = q.pop(0).result()                           # the host blocks on an earlier block's records only
             t4_ = time.perf_counter()
             for i_, d_ in enumerate((t1_ - t0_, t2_ - t1_, t3_ - t2_, t4_ - t3_)):
                 acc[i_] += d_
         t5_ = time.perf_counter()
-        last = pending.result()
+        if overlap:
+            e2e_runner.flush()
+        for ar in q:
+            last = ar.result()
         e2e_phase.update(drain_ms=1e3 * (time.perf_counter() - t5_),
                          gpu_block_ms=[round(a.elapsed_time(b), 2) for a, b in zip(marks[:-1], marks[1:])])
         e2e_phase.update(host_ms_per_step={'pipe_run_launch': 1e3 * acc[0] / n_steps, 'records_async': 1e3 * acc[1] / n_steps,
@@ -298,7 +322,7 @@ def run_ours(args):
         return last
 
     for _ in range(W):
-        out = step_resident()               # same tensor lifetimes as the timed loop (no allocator growth inside it)
+        step_resident()                     # same tensor lifetimes as the timed loop (no allocator growth inside it)
     flush_resident()
     # ---- device-resident timing (value) + per-kernel events for the roofline
     barrier()
@@ -317,11 +341,12 @@ def run_ours(args):
         # (identical) earlier steps take their pair counts from them.
         for e in enn.PROFILE[step_marks[-1] if len(step_marks) < 2 else step_marks[-2]: step_marks[-1]]:
             e[2]['nbr'] = None
-        out = step_resident()
+        step_resident()
         step_marks.append(len(enn.PROFILE))
         step_ev.append(torch.cuda.Event(enable_timing=True))
-        step_ev[-1].record()
+        step_ev[-1].record(runner.main_stream if overlap else torch.cuda.current_stream())
     allrec = flush_resident()               # the last block's gathered records are on the host: the timed region ends here
+    out = res_state['last_out']
     ev1.record()
     barrier()
     launches = int(lib.eyoc_launch_count() - launches0)
@@ -455,7 +480,9 @@ def run_ours(args):
                     + ('; estimator fed planted descriptors (the forward pass still runs and is timed)' if desc_d is not None else ''),
             'config': {'workload': workload_name(args.model), 'pairs_per_gpu': P, 'global_pairs': P * world, 'voxels_per_step_per_gpu': int(coords_np.shape[0]),
                        'parallelism': f'pair-sharded x{world}', 'l2': 'per-step working set (>= 1 GB of level-1 features) exceeds the 126 MB L2; no explicit flush',
-                       'value_mode': 'coordinates, points and index plans resident in HBM', 'conv_mode': enn.CONV_MODE, 'tile_order': bool(enn.TILE_ORDER)},
+                       'value_mode': 'coordinates, points and index plans resident in HBM', 'conv_mode': enn.CONV_MODE, 'tile_order': bool(enn.TILE_ORDER),
+                       'stage_overlap': ('stage 3 of block k (NN + SC2-PCR) on a second stream beside stage 1 of block k+1 (coordinate sets, '
+                                         'kernel maps); the convolutions run alone; fill and drain are inside the timed region') if overlap else 'none'},
             'e2e': {'value': e2e, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(h2d_bytes),
                     'd2h_bytes_per_step': int(rec_hosts[0].numel() * 4), 'ms_per_step': 1e3 * e2e_s / K,
                     'host_phases': e2e_phase.get('host_ms_per_step'), 'drain_ms': e2e_phase.get('drain_ms'),
@@ -497,6 +524,7 @@ def main():
     ap.add_argument('--no-check-gather', action='store_true',
                     help='skip the world > 1 self-check (rank 0 recomputes every rank\'s block and compares the gathered table byte for byte)')
     ap.add_argument('--conv-breakdown', action='store_true')
+    ap.add_argument('--no-overlap', action='store_true', help='run the three stages of every block back to back on one stream')
     ap.add_argument('--e2e-diag', default=None, choices=['prefetch', 'noplan', 'noupload'],
                     help='diagnostic only (the e2e figure is then NOT an end-to-end number): prefetch = every block planned and uploaded before the timed loop')
     ap.add_argument('--no-tile-order', action='store_true')

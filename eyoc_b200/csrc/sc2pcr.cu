@@ -1156,44 +1156,38 @@ seed_kabsch_kernel(FitArgs a, int batch) {
     for (int k = 0; k < 16; ++k) out[k] = T[k];
 }
 
-// Inlier counts of the seed hypotheses (SC2_PCR.py:150-158): 8 seeds per CTA share every point load.
-constexpr int FS = 8;
+// Inlier counts of the seed hypotheses (SC2_PCR.py:150-158): FS seeds per CTA share every point load; their transforms live in
+// registers (the loop is bound by the fp32 pipe: 20 dependent-rounding operations per point and seed, nothing else to issue).
+constexpr int FS = 4;
 __global__ void __launch_bounds__(256)
 seed_fitness_kernel(FitArgs a) {
-    __shared__ __align__(16) f32x2 T2[FS][12];            // every entry of the 3x4 transform twice: operands of the packed math
     __shared__ int cnt[8][FS];
     const int b = blockIdx.y, s0 = blockIdx.x * FS;
     const Pt* P = a.P + (size_t)b * a.n;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < FS * 12) {
-        const int s = min(s0 + tid / 12, a.S - 1);
-        const float t = a.seed_trans[((size_t)b * a.S + s) * 16 + tid % 12];
-        T2[tid / 12][tid % 12] = pack2(t, t);
+    float T[FS][12];
+#pragma unroll
+    for (int k = 0; k < FS; ++k) {
+        const float4* src = reinterpret_cast<const float4*>(a.seed_trans + ((size_t)b * a.S + min(s0 + k, a.S - 1)) * 16);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const float4 v = __ldg(src + q);
+            T[k][4 * q] = v.x; T[k][4 * q + 1] = v.y; T[k][4 * q + 2] = v.z; T[k][4 * q + 3] = v.w;
+        }
     }
-    __syncthreads();
     int c[FS];
 #pragma unroll
     for (int k = 0; k < FS; ++k) c[k] = 0;
-    // two points per thread and iteration in the halves of f32x2 registers (add / mul / fma .rn.f32x2 round each half exactly as
-    // the scalar instructions of apply_T do)
-    for (int j = tid; j < a.n; j += 512) {
-        const bool ok1 = j + 256 < a.n;
-        const Pt p0 = load_pt(P + j), p1 = load_pt(P + (ok1 ? j + 256 : j));
-        const f32x2 sx = pack2(p0.sx, p1.sx), sy = pack2(p0.sy, p1.sy), sz = pack2(p0.sz, p1.sz);
-        const f32x2 tx = pack2(p0.tx, p1.tx), ty = pack2(p0.ty, p1.ty), tz = pack2(p0.tz, p1.tz);
+    for (int j = tid; j < a.n; j += 256) {
+        const Pt p = load_pt(P + j);
 #pragma unroll
         for (int k = 0; k < FS; ++k) {
-            const f32x2* T = T2[k];
-            // R p + t as apply_T: 3-term dot (sequential FMA) then + t
-            const f32x2 x = add2(fma2(T[2], sz, fma2(T[1], sy, mul2(T[0], sx))), T[3]);
-            const f32x2 y = add2(fma2(T[6], sz, fma2(T[5], sy, mul2(T[4], sx))), T[7]);
-            const f32x2 z = add2(fma2(T[10], sz, fma2(T[9], sy, mul2(T[8], sx))), T[11]);
+            float x, y, z;
+            apply_T(T[k], p.sx, p.sy, p.sz, x, y, z);
             // torch.norm(.) < thr  <=>  sum of squares < s0: sqrt_rn is monotonic and s0 (host: sqrt_threshold) is the
             // smallest fp32 whose correctly rounded root reaches thr - the root itself is never formed
-            const f32x2 dx = sub2(x, tx), dy = sub2(y, ty), dz = sub2(z, tz);
-            float q0, q1;
-            unpack2(fma2(dz, dz, fma2(dy, dy, mul2(dx, dx))), q0, q1);
-            c[k] += (int)!(q0 >= a.inlier_s0) + (int)(ok1 && !(q1 >= a.inlier_s0));
+            const float dx = __fsub_rn(x, p.tx), dy = __fsub_rn(y, p.ty), dz = __fsub_rn(z, p.tz);
+            c[k] += !(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))) >= a.inlier_s0);
         }
     }
 #pragma unroll

@@ -78,22 +78,64 @@ class ResUNet2(nn.Module):
         if self.RANGE_CHECK and enn.CONV_MODE == 'f16x3':
             mgr = x.coordinate_manager
             if int(mgr.range_status.item()) & 1:
-                import warnings
-                warnings.warn('activations beyond the fp16 hi/lo range (|x| >= 65504 or non-finite): re-running this forward '
-                              "pass with fp32 activations (CONV_MODE 'tf32x3')")
-                mgr.range_status.zero_()
-                enn.CONV_MODE = 'tf32x3'
-                try:
-                    out = self._forward(x)
-                finally:
-                    enn.CONV_MODE = 'f16x3'
+                out = self.forward_fp32_activations(x)
         return out
 
-    def _forward(self, x):
+    def forward_fp32_activations(self, x):
+        """The fallback of the range guard: the same forward pass through the fp32-activation tensor-core path."""
+        import warnings
+        warnings.warn('activations beyond the fp16 hi/lo range (|x| >= 65504 or non-finite): re-running this forward '
+                      "pass with fp32 activations (CONV_MODE 'tf32x3')")
+        x.coordinate_manager.range_status.zero_()
+        enn.CONV_MODE = 'tf32x3'
+        try:
+            return self._forward(x)
+        finally:
+            enn.CONV_MODE = 'f16x3'
+
+    # ---- the forward pass in two stages, for callers that overlap stage 1 of one block with other work (pipeline.py):
+    #      stage 1 = everything bound by dependent-access latency (first convolution with its neighbour search, kernel maps, tile
+    #      orders), stage 2 = the tensor-core convolutions.  forward(x) == trunk(x, prepare(x)).
+    def prepare(self, x):
+        if self.training:
+            raise NotImplementedError('eyoc_b200 implements the inference path only: call model.eval()')
+        with torch.no_grad():
+            y1 = conv_bn_act(x, self.conv1, self.norm1)
+        self.build_maps(x.coordinate_manager)
+        return y1
+
+    def build_maps(self, mgr):
+        """Queue every kernel map (tile order + tile masks for the tensor-core convolutions) the trunk will ask for: 3^3 maps on
+        strides 1, 2, 4, 8, the strided ones between them and their transposes (model/resunet.py:31-140)."""
+        tiled = enn.TILE_ORDER and enn.CONV_MODE in ('f16x3', 'tf32x3')
+        want = [(1, 1, False), (1, 2, False), (2, 2, False), (2, 4, False), (4, 4, False), (4, 8, False), (8, 8, False),
+                (8, 4, True), (4, 2, True), (2, 1, True)]
+        mgr.ensure_levels(8)
+        for ts_in, ts_out, tr in want:
+            if mgr.num_rows(ts_in) == 0 or mgr.num_rows(ts_out) == 0:
+                continue
+            if tiled:
+                mgr.tiled_map(ts_in, ts_out, 3, transposed=tr)
+                if enn.CONV_MODE == 'f16x3':
+                    mgr.tile_masks(ts_in, ts_out, 3, transposed=tr)
+            else:
+                mgr.kernel_map(ts_in, ts_out, 3, transposed=tr)
+
+    def trunk(self, x, y1):
+        """Stage 2.  Returns (output, pending read of the fp16 range flag or None): the caller resolves the read when
+        convenient and calls forward_fp32_activations(x) if bit 0 is set."""
+        out = self._forward(x, y1)
+        read = None
+        if self.RANGE_CHECK and enn.CONV_MODE == 'f16x3':
+            from ..sparse import _AsyncRead
+            read = _AsyncRead(x.coordinate_manager.range_status)
+        return out, read
+
+    def _forward(self, x, y1=None):
         """model/resunet.py:142-193.  The MEF.relu calls after each block (:146,151,156,161,166,173,180) are
         idempotent (the block already ends in ReLU, residual_block.py:51) and therefore cost nothing here."""
         with torch.no_grad():
-            out_s1 = self.block1(conv_bn_act(x, self.conv1, self.norm1))
+            out_s1 = self.block1(y1 if y1 is not None else conv_bn_act(x, self.conv1, self.norm1))
             out_s2 = self.block2(conv_bn_act(out_s1, self.conv2, self.norm2))
             out_s4 = self.block3(conv_bn_act(out_s2, self.conv3, self.norm3))
             out_s8 = self.block4(conv_bn_act(out_s4, self.conv4, self.norm4))
@@ -162,10 +204,10 @@ class ResUNetExpanded(ResUNet2):
         x = getattr(self, f'block{name}')(x)
         return getattr(self, f'block{name}_2')(getattr(self, f'norm{name}_2')(x))
 
-    def _forward(self, x):
+    def _forward(self, x, y1=None):
         """model/resunet.py:396-486."""
         with torch.no_grad():
-            out_s1 = self._level(conv_bn_act(x, self.conv1, self.norm1), '1')
+            out_s1 = self._level(y1 if y1 is not None else conv_bn_act(x, self.conv1, self.norm1), '1')
             out_s2 = self._level(conv_bn_act(out_s1, self.conv2, self.norm2), '2')
             out_s4 = self._level(conv_bn_act(out_s2, self.conv3, self.norm3), '3')
             out_s8 = self._level(conv_bn_act(out_s4, self.conv4, self.norm4), '4')

@@ -134,14 +134,30 @@ class RegistrationPipeline:
         by the benchmark to give the estimator a realistic inlier ratio with random-init weights); the forward
         pass is executed regardless."""
         plan = plan or self.plan(sizes)
-        dev = coords.device
+        feats_in = ones_features(coords.shape[0], coords.device)   # lib/data_loaders.py:971-972: occupancy-only input
+        F = self.model(SparseTensor(feats_in, coordinates=coords)).F
+        return self.match(F, xyz, sizes, plan, descriptors)
+
+    # ---- the same path in three stages (OverlappedRunner runs stage 1 of block k + 1 beside stage 3 of block k)
+    def prepare(self, coords):
+        """Stage 1: coordinate sets, first convolution (with its neighbour search), kernel maps and tile orders - the part of a
+        block that is bound by dependent-access latency, not by bandwidth or math."""
+        x = SparseTensor(ones_features(coords.shape[0], coords.device), coordinates=coords)
+        return x, self.model.prepare(x)
+
+    def forward(self, prepared):
+        """Stage 2: the tensor-core convolutions.  -> (features [sum N, 32] fp32, pending range-flag read or None, x)."""
+        x, y1 = prepared
+        out, read = self.model.trunk(x, y1)
+        return out.F, read, x
+
+    def match(self, F, xyz, sizes, plan, descriptors=None):
+        """Stage 3: find_corr NN, resampling, match_pair NN, SC2-PCR, inlier labels on the features of stage 2."""
+        dev = F.device
 
         def dv(a):
             return a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
 
-        P = len(sizes)
-        feats_in = ones_features(coords.shape[0], dev)            # lib/data_loaders.py:971-972: occupancy-only input
-        F = self.model(SparseTensor(feats_in, coordinates=coords)).F
         Fm = F if descriptors is None else descriptors
         out = {'features': F}
         if self.run_find_corr:                                   # diagnostic NN of the reference (test_kitti.py:153-154)
@@ -180,6 +196,122 @@ class RegistrationPipeline:
         rec[:, 18] = ids.to(device=rec.device, dtype=torch.float32, non_blocking=True)
         rec[:, 19] = 1.0
         return rec
+
+
+class OverlappedRunner:
+    """Software pipeline over consecutive blocks on two CUDA streams.  Stage 3 of block k (nearest neighbours + SC2-PCR:
+    compute-bound kernels) runs on ``match_stream`` while stage 1 of block k + 1 (coordinate sets, kernel maps, tile orders:
+    small kernels bound by dependent-access latency) runs on the caller's stream; the two fill each other's idle issue slots.
+    Stage 2 (the tensor-core convolutions, bandwidth-bound) always has the GPU to itself: it is queued behind an event that
+    stage 3 of the previous block records.  ``submit`` returns the results of the PREVIOUS block; ``flush`` those of the last.
+
+        runner = OverlappedRunner(pipe)
+        for blk in blocks:
+            out = runner.submit(**blk)          # None for the first block
+        out = runner.flush()
+
+    ``before_match`` / ``after_match`` (optional callables) run inside the match stream's context right before / after
+    stage 3 is queued - the place to make that stream wait for uploads, to build the result records, and to release input
+    buffers.  ``after_match(out)`` may return a replacement for ``out``."""
+
+    def __init__(self, pipe, device=None):
+        self.pipe = pipe
+        # stages 1 + 2 on a HIGH-priority stream: while a stage-3 kernel with tens of thousands of CTAs is running, the CTAs of
+        # the small stage-1 kernels are dispatched first whenever an SM has room (same-priority kernels would queue behind it)
+        self.main_stream = torch.cuda.Stream(device=device, priority=-1)
+        self.match_stream = torch.cuda.Stream(device=device)
+        self._pending = None
+        self._match_done = None
+        self.trace = None            # set to a list: per block a dict of timing events (stage boundaries on both streams)
+
+    def _ev(self, stream):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        return e
+
+    def _match_pending(self):
+        p, self._pending = self._pending, None
+        if p is None:
+            return None
+        with torch.cuda.stream(self.match_stream):
+            self.match_stream.wait_event(p['inputs_ready'])
+            self.match_stream.wait_event(p['conv_done'])
+            if p['before_match'] is not None:
+                p['before_match']()
+            if p['trace'] is not None:
+                p['trace']['match_start'] = self._ev(self.match_stream)
+            out = self.pipe.match(p['F'], p['xyz'], p['sizes'], p['plan'], p['descriptors'])
+            if p['after_match'] is not None:
+                r = p['after_match'](out)
+                out = out if r is None else r
+            self._match_done = torch.cuda.Event()
+            self._match_done.record(self.match_stream)
+            if p['trace'] is not None:
+                p['trace']['match_end'] = self._ev(self.match_stream)
+        p['F'].record_stream(self.match_stream)                  # allocated on the main stream, read on the match stream
+        return out, p
+
+    def _resolve_range(self, out, p):
+        """The fp16 range flag of the block whose matching was just queued: its convolutions finished long ago, so the read
+        does not wait.  A flagged block is redone synchronously through the fp32-activation path (rare, not overlapped)."""
+        if p['read'] is not None and int(p['read'].get()[0]) & 1:
+            torch.cuda.current_stream().wait_stream(self.match_stream)
+            F = self.pipe.model.forward_fp32_activations(p['x']).F
+            redo = self.pipe.match(F, p['xyz'], p['sizes'], p['plan'], p['descriptors'])
+            if p['after_match'] is not None:                     # the hooks see the recomputed block as well
+                r = p['after_match'](redo)
+                redo = redo if r is None else r
+            return redo
+        return out
+
+    def submit(self, coords, xyz, sizes, plan=None, descriptors=None, before_match=None, after_match=None):
+        """Queue stage 3 of the previous block and stages 1 + 2 of this one.  Returns the previous block's result dict (None for
+        the first block); its tensors are produced on ``match_stream`` - consume them in ``after_match``, or after
+        ``match_stream.synchronize()`` / ``flush()``."""
+        ready = torch.cuda.Event()
+        ready.record()                                           # the inputs are complete on the caller's stream
+        prev = self._match_pending()                             # stage 3 of the previous block -> match stream
+        plan = plan or self.pipe.plan(sizes)
+        out = None
+        with torch.cuda.stream(self.main_stream):
+            self.main_stream.wait_event(ready)
+            tr = None
+            if self.trace is not None:
+                tr = dict(prep_start=self._ev(self.main_stream))
+                self.trace.append(tr)
+            prepared = self.pipe.prepare(coords)                 # stage 1 of this block, beside it
+            if tr is not None:
+                tr['prep_end'] = self._ev(self.main_stream)
+            if prev is not None:
+                out = self._resolve_range(*prev)
+            if self._match_done is not None:
+                self.main_stream.wait_event(self._match_done)    # stage 2 runs alone
+            if tr is not None:
+                tr['conv_start'] = self._ev(self.main_stream)
+            F, read, x = self.pipe.forward(prepared)
+            done = torch.cuda.Event()
+            done.record(self.main_stream)
+            if tr is not None:
+                tr['conv_end'] = self._ev(self.main_stream)
+        for t in (coords, xyz, descriptors):
+            if isinstance(t, torch.Tensor):
+                t.record_stream(self.main_stream)
+                t.record_stream(self.match_stream)
+        self._pending = dict(F=F, read=read, x=x, xyz=xyz, sizes=sizes, plan=plan, descriptors=descriptors, conv_done=done,
+                             inputs_ready=ready, before_match=before_match, after_match=after_match, trace=tr)
+        return out
+
+    def flush(self):
+        """Queue stage 3 of the last block; the caller's stream then waits for both streams of the runner."""
+        prev = self._match_pending()
+        out = None
+        if prev is not None:
+            with torch.cuda.stream(self.main_stream):
+                out = self._resolve_range(*prev)
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(self.match_stream)
+        cur.wait_stream(self.main_stream)
+        return out
 
 
 class PlanPrefetcher:

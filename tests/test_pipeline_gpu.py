@@ -82,3 +82,44 @@ def test_pipeline_vs_oracle_end_to_end():
     assert torch.equal(labels.cpu(), labels_o)                                       # bit-exact inlier mask
     assert float(torch.linalg.norm(T[0, :3, :3].cpu() - T_o[0, :3, :3])) < 1e-4
     assert float(torch.linalg.norm(T[0, :3, 3].cpu() - T_o[0, :3, 3])) < 1e-3
+
+
+def test_overlapped_runner_equals_sequential_runs():
+    """pipeline.OverlappedRunner (stage 3 of block k on a second stream beside stage 1 of block k + 1) returns, block by block,
+    the bits of sequential pipe.run calls: same features, correspondences, poses, labels - over several different blocks."""
+    from eyoc_b200 import synth
+    from eyoc_b200.pipeline import OverlappedRunner, RegistrationPipeline
+    from eyoc_b200.model import load_model
+    from eyoc_b200.scripts.SC2_PCR.SC2_PCR import Matcher
+    from oracle import resunet_oracle as RO
+    dev = torch.device('cuda')
+    model = load_model('ResUNetBN2C')(1, 32, bn_momentum=0.05, normalize_feature=True, conv1_kernel_size=5, D=3)
+    model.load_state_dict(RO.make_state_dict(1, 32, 5, seed=2))
+    m = Matcher(inlier_threshold=0.6, num_node=2000, use_mutual=False, d_thre=0.1, num_iterations=20, ratio=0.2,
+                nms_radius=0.6, max_points=8000, k1=30, k2=20)
+    pipe = RegistrationPipeline(model.to(dev).eval(), m, subsample_size=2000, num_sample=3000)
+    blocks = []
+    for b in range(4):
+        pairs = [synth.make_pair(100 + 3 * b + i, distance=6.0 + i, az_step_deg=1.0) for i in range(2 + b % 2)]
+        coords, xyz, desc, sizes = synth.collate_pairs(pairs)
+        rng = np.random.default_rng(b)
+        desc = np.concatenate([d for p_ in pairs for d in synth.planted_descriptors(p_['xyz0'], p_['xyz1'], p_['T_gt'], rng, sigma=0.08)[:2]]).astype(np.float32)
+        blocks.append(dict(coords=torch.from_numpy(coords).to(dev), xyz=torch.from_numpy(xyz).to(dev), sizes=sizes,
+                           descriptors=torch.from_numpy(desc).to(dev)))
+    np.random.seed(3)
+    plans = [pipe.plan(b['sizes']) for b in blocks]
+    seq = [pipe.run(b['coords'], b['xyz'], b['sizes'], plan=p, descriptors=b['descriptors']) for b, p in zip(blocks, plans)]
+    torch.cuda.synchronize()
+    runner = OverlappedRunner(pipe, dev)
+    got, seen = [], []
+    for b, p in zip(blocks, plans):
+        o = runner.submit(b['coords'], b['xyz'], b['sizes'], plan=p, descriptors=b['descriptors'],
+                          after_match=lambda out: seen.append(int(out['labels'].shape[0])))
+        if o is not None:
+            got.append(o)
+    got.append(runner.flush())
+    torch.cuda.synchronize()
+    assert len(got) == len(seq) == 4 and seen == [len(b['sizes']) for b in blocks]
+    for a, b in zip(seq, got):
+        for key in ('features', 'trans', 'labels', 'fitness', 'src_corr', 'tgt_corr', 'tgt_corr_idx', 'find_corr_tgt'):
+            assert torch.equal(a[key], b[key]), key
