@@ -56,7 +56,7 @@ def lib():
         for name in ('eyoc_knn1_workspace_bytes', 'eyoc_sc2pcr_workspace_bytes', 'eyoc_downsample_workspace_bytes',
                      'eyoc_tile_order_workspace_bytes', 'eyoc_conv_weight_image_floats', 'eyoc_voxelize_workspace_bytes',
                      'eyoc_convh_weight_image_halves', 'eyoc_knn1_tc_workspace_bytes', 'eyoc_pick_seeds_workspace_bytes',
-                     'eyoc_power_iteration_workspace_bytes', 'eyoc_irls_workspace_bytes', 'eyoc_knn2_workspace_bytes', 'eyoc_stem_conv_workspace_bytes'):
+                     'eyoc_power_iteration_workspace_bytes', 'eyoc_irls_workspace_bytes', 'eyoc_knn2_workspace_bytes', 'eyoc_stem_conv_workspace_bytes', 'eyoc_instance_norm_workspace_bytes'):
             if hasattr(_lib, name):
                 getattr(_lib, name).restype = c_size_t
     return _lib

@@ -8,7 +8,7 @@ import sys
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ['capi.cu', 'knn.cu', 'sc2pcr.cu', 'coordmap.cu', 'sparse_conv.cu', 'sparse_conv_tc.cu', 'sparse_conv_h.cu', 'irls.cu', 'host_plan.cu', 'gather4_probe.cu']
+SOURCES = ['capi.cu', 'knn.cu', 'sc2pcr.cu', 'coordmap.cu', 'sparse_conv.cu', 'sparse_conv_tc.cu', 'sparse_conv_h.cu', 'irls.cu', 'host_plan.cu', 'gather4_probe.cu', 'instance_norm.cu']
 LIB = os.path.join(os.path.dirname(HERE), 'libeyoc_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',

@@ -1,4 +1,4 @@
-"""Residual block with the reference's model/residual_block.py:13-77 interface (BN variant)."""
+"""Residual block with the reference's model/residual_block.py:13-77 interface (BN and IN variants)."""
 import torch.nn as nn
 
 from ..nn import MinkowskiConvolution, conv_bn_act
@@ -29,10 +29,16 @@ class BasicBlockBN(BasicBlockBase):
     NORM_TYPE = 'BN'
 
 
+class BasicBlockIN(BasicBlockBase):
+    """model/residual_block.py:60-61: conv -> instance norm -> ReLU -> conv -> instance norm -> + x -> ReLU (conv_bn_act runs
+    the convolution alone and fuses residual + ReLU into the normalisation pass)."""
+    NORM_TYPE = 'IN'
+
+
 def get_block(norm_type, inplanes, planes, stride=1, dilation=1, downsample=None, bn_momentum=0.1, D=3):
     if norm_type == 'BN':
         return BasicBlockBN(inplanes, planes, stride, dilation, downsample, bn_momentum, D)
     elif norm_type == 'IN':
-        raise NotImplementedError('InstanceNorm blocks are not on the inference hot path')
+        return BasicBlockIN(inplanes, planes, stride, dilation, downsample, bn_momentum, D)
     else:
         raise ValueError(f'Type {norm_type}, not defined')

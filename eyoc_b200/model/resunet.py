@@ -184,6 +184,32 @@ class ResUNetFatBN(ResUNet2):
     TR_CHANNELS = [None, 128, 128, 128, 256]
 
 
+class ResUNetIN2(ResUNet2):
+    """model/resunet.py:229-232: batch norm after the strided / transposed convolutions, instance norm inside the blocks."""
+    NORM_TYPE = 'BN'
+    BLOCK_NORM_TYPE = 'IN'
+
+
+class ResUNetIN2B(ResUNetBN2B):
+    NORM_TYPE = 'BN'
+    BLOCK_NORM_TYPE = 'IN'
+
+
+class ResUNetIN2C(ResUNetBN2C):
+    NORM_TYPE = 'BN'
+    BLOCK_NORM_TYPE = 'IN'
+
+
+class ResUNetIN2D(ResUNetBN2D):
+    NORM_TYPE = 'BN'
+    BLOCK_NORM_TYPE = 'IN'
+
+
+class ResUNetIN2E(ResUNetBN2E):
+    NORM_TYPE = 'BN'
+    BLOCK_NORM_TYPE = 'IN'
+
+
 class ResUNetExpanded(ResUNet2):
     """model/resunet.py:254-486: every level runs two residual blocks with a stand-alone norm in between
     (norm -> block -> ReLU -> norm_2 -> block_2 -> ReLU).  Same sub-module names / state-dict keys as the reference."""

@@ -122,6 +122,50 @@ class MinkowskiBatchNorm(nn.Module):
 #   'tf32x3' : tcgen05 tensor cores, 3-term TF32 split, fp32 activations (csrc/sparse_conv_tc.cu)
 #   'fp32'   : fp32 FMA register-tile kernel (csrc/sparse_conv.cu); also the path of everything that does not qualify
 CONV_MODE = 'f16x3'
+class MinkowskiInstanceNorm(nn.Module):
+    """ME.MinkowskiInstanceNorm(num_features): per cloud and channel (x - mean) / sqrt(var + 1e-8) * weight + bias, biased
+    variance, parameters of shape [1, C] (model/common.py:7-8; used by BasicBlockIN, model/residual_block.py:60-61)."""
+    EPS = 1e-8
+
+    def __init__(self, num_features, dimension=-1):
+        super().__init__()
+        self.num_features = num_features
+        self.weight = nn.Parameter(torch.ones(1, num_features))
+        self.bias = nn.Parameter(torch.zeros(1, num_features))
+
+    def forward(self, x, residual=None, relu=False):
+        return instance_norm(x, self, residual=residual, relu=relu)
+
+
+def instance_norm(x, norm, residual=None, relu=False):
+    """eyoc_instance_norm on a SparseTensor: split-half features stay split-half; the residual add and the ReLU of the residual
+    block are fused into the apply pass."""
+    mgr = x.coordinate_manager
+    ts = x.coordinate_map_key.tensor_stride
+    mgr._check_status()
+    lv = mgr.levels[ts]
+    packed = x._Fh is not None and CONV_MODE == 'f16x3'
+    src = x._Fh if packed else x.F.contiguous()
+    c = x.num_channels
+    res = None
+    if residual is not None:
+        res = residual.Fh if packed else residual.F.contiguous()
+    out = torch.empty_like(src)
+    B = mgr.max_batch + 1
+    lib = _C.lib()
+    _C.require_cuda(src, res, norm.weight, norm.bias)
+    ws = torch.empty(lib.eyoc_instance_norm_workspace_bytes(_C.c_int(B), _C.c_int(c)), dtype=torch.uint8, device=src.device)
+    with torch.cuda.device(src.device):
+        _C.check(lib.eyoc_instance_norm(_C.ptr(src), _C.c_int(int(packed)), _C.ptr(lv.coords), _C.c_int64(lv.n), _C.c_int(c), _C.c_int(B),
+                                        _C.ptr(norm.weight.detach().reshape(-1).contiguous()),
+                                        _C.ptr(norm.bias.detach().reshape(-1).contiguous()), _C.c_float(norm.EPS), _C.ptr(res),
+                                        _C.c_int(int(packed)), _C.c_int(int(relu)), _C.ptr(out), _C.c_int(int(packed)),
+                                        _C.ptr(mgr.range_status), _C.ptr(ws), _C.c_size_t(ws.numel()), _C.stream()))
+    if packed:
+        return SparseTensor(features_xh=out, coordinate_map_key=x.coordinate_map_key, coordinate_manager=mgr)
+    return SparseTensor(out, coordinate_map_key=x.coordinate_map_key, coordinate_manager=mgr)
+
+
 # Tensor-core convolutions tile their output rows in (cloud group, neighbour pattern) order (CoordinateManager.tiled_map)
 TILE_ORDER = True
 # The 1-channel first convolution runs fused with its neighbour search (CoordinateManager.stem_conv)
@@ -254,6 +298,13 @@ def conv_bn_act(x, conv, norm=None, residual=None, relu=False, l2norm=False, ski
     x, skip, residual are SparseTensors; returns a SparseTensor on the output coordinate map.  In 'f16x3' mode the
     convolutions that qualify read and write split-half features (SparseTensor.Fh); ``.F`` of the result converts on
     first access, the normalised network output is written as fp32 directly."""
+    if isinstance(norm, MinkowskiInstanceNorm):
+        # instance statistics need the whole convolution output first: conv alone, then normalise (+ residual, ReLU) in one pass
+        raw = conv_bn_act(x, conv, None, skip=skip)
+        y = instance_norm(raw, norm, residual=residual, relu=relu)
+        if l2norm:
+            raise NotImplementedError('l2norm after an instance norm is not a layer of the reference models')
+        return y
     mgr = x.coordinate_manager
     ts_in = x.coordinate_map_key.tensor_stride
     ts_out = conv.out_stride(ts_in)

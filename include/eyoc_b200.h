@@ -209,6 +209,16 @@ int eyoc_sparse_conv_tc(const float* in0, int c0, const float* in1, int c1, cons
                         const float* shift, const float* residual, int relu, int l2norm, float* out, int cout,
                         eyoc_stream_t stream);
 
+/* ME.MinkowskiInstanceNorm as the reference's BasicBlockIN uses it (model/common.py:7-8, model/residual_block.py:60-61; the
+ * ResUNetIN2* variants of model/resunet.py:229-251): per cloud (coords[:, 0], 0 .. num_clouds - 1) and channel,
+ * y = (x - mean) / sqrt(var + eps) * weight + bias with the biased variance of the cloud's rows; `residual` (optional) is added
+ * and ReLU applied afterwards (model/residual_block.py:47-51).  x / residual / out: fp32 [n, c] rows or split-half rows
+ * (*_packed); c in {32, 64, 128, 256}; weight / bias [c] or NULL.  Three bandwidth-bound passes, fp64 statistics. */
+size_t eyoc_instance_norm_workspace_bytes(int num_clouds, int c);
+int eyoc_instance_norm(const void* x, int x_packed, const int32_t* coords, int64_t n, int c, int num_clouds, const float* weight,
+                       const float* bias, float eps, const void* residual, int residual_packed, int relu, void* out,
+                       int out_packed, int32_t* range_status, void* workspace, size_t workspace_bytes, eyoc_stream_t stream);
+
 /* The network's first convolution (reference model/resunet.py:31-37 `conv1`: ME.MinkowskiConvolution(1, 32, kernel_size=5,
  * stride=1) + model/resunet.py:38 `norm1` + ReLU of :147-150) fused with its own neighbour search on the stride-1 coordinate
  * set: `in` [n] is the single input channel (NULL = every value is 1.0, the occupancy-only input the reference feeds:

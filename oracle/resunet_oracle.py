@@ -133,10 +133,33 @@ def _bn(x, sd, name):
                         sd[name + '.bn.weight'], sd[name + '.bn.bias'], False, 0.0, BN_EPS)
 
 
-def _block(x, sd, name, nbr):
-    """model/residual_block.py:37-53."""
-    out = F.relu(_bn(sparse_conv(x, sd[name + '.conv1.kernel'], nbr), sd, name + '.norm1'))
-    out = _bn(sparse_conv(out, sd[name + '.conv2.kernel'], nbr), sd, name + '.norm2')
+IN_EPS = 1e-8
+
+
+def _in(x, sd, name, batch):
+    """ME.MinkowskiInstanceNorm (model/common.py:7-8) restated from MinkowskiEngine 0.5's MinkowskiNormalization.py
+    [ME-upstream, not runnable here]: per cloud, mean = global average pool of x, var = global average pool of (x - mean)^2
+    (biased), out = (x - mean) * (1 / sqrt(var + 1e-8)) * weight + bias with [1, C] parameters."""
+    out = torch.empty_like(x)
+    batch = torch.as_tensor(np.asarray(batch))
+    for b in torch.unique(batch).tolist():
+        sel = batch == b
+        xb = x[sel]
+        mean = xb.double().mean(0).to(x.dtype)
+        centred = xb - mean
+        var = (centred.double() ** 2).mean(0).to(x.dtype)
+        out[sel] = centred * (1.0 / torch.sqrt(var + IN_EPS))
+    return out * sd[name + '.weight'].reshape(1, -1) + sd[name + '.bias'].reshape(1, -1)
+
+
+def _norm(x, sd, name, batch):
+    return _bn(x, sd, name) if (name + '.bn.weight') in sd else _in(x, sd, name, batch)
+
+
+def _block(x, sd, name, nbr, batch=None):
+    """model/residual_block.py:37-53 (BasicBlockBN / BasicBlockIN by the keys the state dict holds)."""
+    out = F.relu(_norm(sparse_conv(x, sd[name + '.conv1.kernel'], nbr), sd, name + '.norm1', batch))
+    out = _norm(sparse_conv(out, sd[name + '.conv2.kernel'], nbr), sd, name + '.norm2', batch)
     return F.relu(out + x)
 
 
@@ -156,24 +179,25 @@ def resunet_forward(coords, feats, sd, normalize_feature=True, conv1_kernel_size
     """model/resunet.py:142-193.  coords [N,4] int (b,x,y,z), feats [N,Cin] -> F [N,32]."""
     maps = maps or build_maps(coords, conv1_kernel_size)
     s1, dn, up = maps['s1'], maps['down'], maps['up']
+    bt = [m.coords[:, 0] for m in maps['levels']]              # batch column per level (instance-norm blocks)
     x = torch.as_tensor(feats)
     o1 = _bn(sparse_conv(x, sd['conv1.kernel'], maps['k5']), sd, 'norm1')
-    o1 = _block(o1, sd, 'block1', s1[0]); out = F.relu(o1)
+    o1 = _block(o1, sd, 'block1', s1[0], bt[0]); out = F.relu(o1)
     o2 = _bn(sparse_conv(out, sd['conv2.kernel'], dn[0]), sd, 'norm2')
-    o2 = _block(o2, sd, 'block2', s1[1]); out = F.relu(o2)
+    o2 = _block(o2, sd, 'block2', s1[1], bt[1]); out = F.relu(o2)
     o4 = _bn(sparse_conv(out, sd['conv3.kernel'], dn[1]), sd, 'norm3')
-    o4 = _block(o4, sd, 'block3', s1[2]); out = F.relu(o4)
+    o4 = _block(o4, sd, 'block3', s1[2], bt[2]); out = F.relu(o4)
     o8 = _bn(sparse_conv(out, sd['conv4.kernel'], dn[2]), sd, 'norm4')
-    o8 = _block(o8, sd, 'block4', s1[3]); out = F.relu(o8)
+    o8 = _block(o8, sd, 'block4', s1[3], bt[3]); out = F.relu(o8)
 
     out = _bn(sparse_conv(out, sd['conv4_tr.kernel'], up[2]), sd, 'norm4_tr')
-    o4t = F.relu(_block(out, sd, 'block4_tr', s1[2]))
+    o4t = F.relu(_block(out, sd, 'block4_tr', s1[2], bt[2]))
     out = torch.cat([o4t, o4], 1)
     out = _bn(sparse_conv(out, sd['conv3_tr.kernel'], up[1]), sd, 'norm3_tr')
-    o2t = F.relu(_block(out, sd, 'block3_tr', s1[1]))
+    o2t = F.relu(_block(out, sd, 'block3_tr', s1[1], bt[1]))
     out = torch.cat([o2t, o2], 1)
     out = _bn(sparse_conv(out, sd['conv2_tr.kernel'], up[0]), sd, 'norm2_tr')
-    o1t = F.relu(_block(out, sd, 'block2_tr', s1[0]))
+    o1t = F.relu(_block(out, sd, 'block2_tr', s1[0], bt[0]))
     out = torch.cat([o1t, o1], 1)
     out = F.relu(out @ sd['conv1_tr.kernel'])                      # 1x1 conv (Appendix B.6)
     out = out @ sd['final.kernel'] + sd['final.bias']

@@ -247,3 +247,85 @@ def test_forward_expanded_variant_vs_oracle():
     want = RO.resunet_expanded_forward(coords, feats, sd, True, 5)
     got = model(SparseTensor(feats.cuda(), coordinates=torch.from_numpy(coords).cuda())).F.cpu()
     assert float((got - want).abs().max()) <= 1e-5, float((got - want).abs().max())
+
+
+@pytest.mark.parametrize('mode', ['f16x3', 'tf32x3'])
+def test_forward_instance_norm_variant_vs_oracle(mode):
+    """ResUNetIN2C (model/resunet.py:239-241): batch norm on the trunk, ME.MinkowskiInstanceNorm inside every residual block
+    (BasicBlockIN) - the convolution runs alone and eyoc_instance_norm fuses the block's residual add and ReLU.  Three clouds of
+    different sizes in one batch: the statistics are per cloud."""
+    from eyoc_b200 import nn as enn
+    from eyoc_b200.model import load_model
+    from eyoc_b200.sparse import SparseTensor
+    from oracle import resunet_oracle as RO
+    from tests.test_resunet_gpu import _cloud
+    coords = np.concatenate([_cloud(1800, 4, batch=2), _cloud(700, 9, batch=1) + np.array([2, 0, 0, 0])]).astype(np.int32)
+    feats = torch.ones((len(coords), 1), dtype=torch.float32)
+    torch.manual_seed(4)
+    model = load_model('ResUNetIN2C')(1, 32, bn_momentum=0.05, normalize_feature=True, conv1_kernel_size=5, D=3)
+    g = torch.Generator().manual_seed(12)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+                m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            if isinstance(m, enn.MinkowskiInstanceNorm):
+                m.weight.copy_(torch.rand(1, m.num_features, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(1, m.num_features, generator=g) * 0.1)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    assert sd['block1.norm1.weight'].shape == (1, 32) and 'block1.norm1.bn.weight' not in sd and 'norm1.bn.weight' in sd
+    want = RO.resunet_forward(coords, feats, sd, True, 5)
+    model = model.cuda().eval()
+    old = enn.CONV_MODE
+    try:
+        enn.CONV_MODE = mode
+        got = model(SparseTensor(feats.cuda(), coordinates=torch.from_numpy(coords).cuda())).F.cpu()
+    finally:
+        enn.CONV_MODE = old
+    assert float((got - want).abs().max()) <= 2e-5, float((got - want).abs().max())
+
+
+@pytest.mark.parametrize('c', [32, 256])
+@pytest.mark.parametrize('packed', [False, True])
+def test_instance_norm_kernel_vs_fp64(c, packed):
+    """eyoc_instance_norm alone: rows of five clouds in shuffled order (a CTA's 256-row chunk then holds many clouds: the
+    shared-memory slots and the direct global path both run), one cloud with a single row, residual + ReLU fused."""
+    from eyoc_b200 import _C, nn as enn
+    from eyoc_b200.sparse import xh_pack, xh_unpack
+    rng = np.random.default_rng(c)
+    n = 5000
+    batch = rng.choice(5, n, p=[0.5, 0.3, 0.15, 0.0498, 0.0002]).astype(np.int32)
+    batch[17] = 4
+    coords = np.zeros((n, 4), np.int32)
+    coords[:, 0] = batch
+    x = (rng.normal(size=(n, c)) * rng.uniform(0.1, 30, c) + rng.normal(size=c) * 5).astype(np.float32)
+    res = rng.normal(size=(n, c)).astype(np.float32)
+    w, b = rng.uniform(0.5, 1.5, c).astype(np.float32), rng.normal(size=c).astype(np.float32)
+    xd, rd = torch.from_numpy(x).cuda(), torch.from_numpy(res).cuda()
+    if packed:
+        xd, rd = xh_pack(xd), xh_pack(rd)
+        x, res = xh_unpack(xd).cpu().numpy(), xh_unpack(rd).cpu().numpy()          # what the kernel really reads
+    out = torch.empty_like(xd)
+    lib = _C.lib()
+    ws = torch.empty(lib.eyoc_instance_norm_workspace_bytes(5, c), dtype=torch.uint8, device='cuda')
+    st = torch.zeros(1, dtype=torch.int32, device='cuda')
+    cd, wd, bd = torch.from_numpy(coords).cuda(), torch.from_numpy(w).cuda(), torch.from_numpy(b).cuda()   # alive across the call
+    _C.check(lib.eyoc_instance_norm(_C.ptr(xd), int(packed), _C.ptr(cd), _C.c_int64(n), c, 5,
+                                    _C.ptr(wd), _C.ptr(bd), _C.c_float(1e-8),
+                                    _C.ptr(rd), int(packed), 1, _C.ptr(out), int(packed), _C.ptr(st), _C.ptr(ws),
+                                    _C.c_size_t(ws.numel()), _C.stream()))
+    got = (xh_unpack(out) if packed else out).cpu().numpy().astype(np.float64)
+    want = np.empty((n, c))
+    for k in range(5):
+        sel = batch == k
+        xb = x[sel].astype(np.float64)
+        mu = xb.mean(0)
+        var = ((xb - mu) ** 2).mean(0)
+        want[sel] = (xb - mu) / np.sqrt(var + 1e-8) * w + b
+    want = np.maximum(want + res, 0.0)
+    tol = 3e-5 if not packed else 2e-4
+    big = np.abs(want) < 1e3                     # the single-row cloud divides by sqrt(1e-8): compare it apart
+    assert np.abs(got - want)[big].max() <= tol * max(1.0, np.abs(want[big]).max()), np.abs(got - want)[big].max()
+    assert int(st.item()) == 0

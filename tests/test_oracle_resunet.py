@@ -55,3 +55,25 @@ def test_forward_shapes_and_unit_norm():
     assert F.shape == (len(c), 32)
     assert float((F.norm(dim=1) - 1).abs().max()) < 1e-5
     assert sd['conv1.kernel'].shape == (125, 1, 32) and sd['conv1_tr.kernel'].shape == (96, 64)
+
+
+def test_instance_norm_statement_matches_torch_instance_norm():
+    """oracle._in (the restated ME.MinkowskiInstanceNorm) == torch.nn.functional.instance_norm per cloud (biased variance,
+    eps inside the root), then the [1, C] affine."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from oracle import resunet_oracle as RO
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(300, 16, generator=g) * 3 + 1
+    batch = np.repeat([0, 1, 2], [120, 100, 80])
+    perm = torch.randperm(300, generator=g)
+    x, batch = x[perm], batch[perm.numpy()]
+    sd = {'n.weight': torch.rand(1, 16, generator=g) + 0.5, 'n.bias': torch.randn(1, 16, generator=g)}
+    got = RO._in(x, sd, 'n', batch)
+    want = torch.empty_like(x)
+    for b in range(3):
+        sel = torch.from_numpy(batch == b)
+        want[sel] = F.instance_norm(x[sel].T[None], eps=RO.IN_EPS)[0].T
+    want = want * sd['n.weight'] + sd['n.bias']
+    assert float((got - want).abs().max()) < 1e-5
