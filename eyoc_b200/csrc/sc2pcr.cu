@@ -336,6 +336,45 @@ csr_fill_kernel(const Pt* __restrict__ P, const uint32_t* __restrict__ hard, int
     }
 }
 
+// The single-pass form of csr_fill_kernel (every lane walks the bits of its own word and evaluates the SC value on the spot):
+// kept as the reference the two-pass kernel is tested against bit for bit (eyoc_debug_sc2_reference_kernels bit 0).
+__global__ void __launch_bounds__(256)
+csr_fill_serial_kernel(const Pt* __restrict__ P, const uint32_t* __restrict__ hard, int n, int W, float d_sq, Csr csr) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n || !csr.ok[b]) return;
+    P += (size_t)b * n;
+    const uint32_t* row = hard + ((size_t)b * n + i) * W;
+    uint16_t* cols = csr.cols + (size_t)b * csr.cap;
+    float* vals = csr.vals + (size_t)b * csr.cap;
+    uint32_t base = csr.rowptr[(size_t)b * (n + 1) + i];
+    const Pt me = load_pt(P + i);
+    for (int w0 = 0; w0 < W; w0 += 32) {
+        const int w = w0 + lane;
+        uint32_t m = w < W ? row[w] : 0u;
+        const int c = __popc(m);
+        int x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        uint32_t pos = base + (uint32_t)(x - c);
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            const int j = w * 32 + bit;
+            const float cd = cross_dist(me, load_pt(P + j));
+            cols[pos] = (uint16_t)j;
+            vals[pos] = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fmul_rn(cd, cd), d_sq)), 0.f);
+            ++pos;
+        }
+        base += (uint32_t)__shfl_sync(0xffffffffu, x, 31);
+    }
+}
+
+int g_sc2_reference_kernels = 0;    // eyoc_debug_sc2_reference_kernels: bit 0 = csr_fill_serial_kernel, bit 1 = seed_fitness_shared_kernel
+
 // One launch per iteration; warp per row.  The last CTA of each pair normalises, applies the torch.allclose
 // stopping rule and publishes the iteration count; later launches exit at once when done.
 struct PowerState {
@@ -1203,6 +1242,47 @@ seed_fitness_kernel(FitArgs a) {
     }
 }
 
+// The previous form of seed_fitness_kernel (8 seeds per CTA, transforms in shared memory): the reference the register version
+// is tested against (eyoc_debug_sc2_reference_kernels bit 1).
+__global__ void __launch_bounds__(256)
+seed_fitness_shared_kernel(FitArgs a) {
+    constexpr int FS8 = 8;
+    __shared__ float T[FS8][12];
+    __shared__ int cnt[8][FS8];
+    const int b = blockIdx.y, s0 = blockIdx.x * FS8;
+    const Pt* P = a.P + (size_t)b * a.n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < FS8 * 12) {
+        const int s = min(s0 + tid / 12, a.S - 1);
+        T[tid / 12][tid % 12] = a.seed_trans[((size_t)b * a.S + s) * 16 + tid % 12];
+    }
+    __syncthreads();
+    int c[FS8];
+#pragma unroll
+    for (int k = 0; k < FS8; ++k) c[k] = 0;
+    for (int j = tid; j < a.n; j += 256) {
+        const Pt p = load_pt(P + j);
+#pragma unroll
+        for (int k = 0; k < FS8; ++k) {
+            float x, y, z;
+            apply_T(T[k], p.sx, p.sy, p.sz, x, y, z);
+            const float dx = __fsub_rn(x, p.tx), dy = __fsub_rn(y, p.ty), dz = __fsub_rn(z, p.tz);
+            c[k] += !(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))) >= a.inlier_s0);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < FS8; ++k) {
+        const int v = warp_sum_i(c[k]);
+        if (lane == 0) cnt[warp][k] = v;
+    }
+    __syncthreads();
+    if (tid < FS8 && s0 + tid < a.S) {
+        int v = 0;
+        for (int w = 0; w < 8; ++w) v += cnt[w][tid];
+        a.fitness[(size_t)b * a.S + s0 + tid] = (float)v;
+    }
+}
+
 // ------------------------------------------------------------------------ best seed + post_refinement + labels
 struct RefineArgs {
     const Pt* P;
@@ -1534,7 +1614,8 @@ extern "C" int eyoc_sc2pcr(const float* src, const float* tgt, int batch, int n,
             EYOC_LAUNCH_CHECK();
             csr_scan_kernel<<<batch, 1024, 0, stream>>>(csr.rowptr, n, csr.cap, csr.ok);
             EYOC_LAUNCH_CHECK();
-            csr_fill_kernel<<<dim3((n + 7) / 8, batch), 256, 0, stream>>>(P, hard, n, W, cfg->d_thre_sq, csr);
+            if (g_sc2_reference_kernels & 1) csr_fill_serial_kernel<<<dim3((n + 7) / 8, batch), 256, 0, stream>>>(P, hard, n, W, cfg->d_thre_sq, csr);
+            else csr_fill_kernel<<<dim3((n + 7) / 8, batch), 256, 0, stream>>>(P, hard, n, W, cfg->d_thre_sq, csr);
             EYOC_LAUNCH_CHECK();
             const int rows_per = (n + PF_C - 1) / PF_C, n_pad = (n + 3) & ~3;
             const size_t pf_fixed = (size_t)3 * n_pad * 4 + (size_t)((rows_per + 1 + 3) & ~3) * 4;
@@ -1581,7 +1662,8 @@ extern "C" int eyoc_sc2pcr(const float* src, const float* tgt, int batch, int n,
         }
         seed_kabsch_kernel<<<(unsigned)((batch * S + 127) / 128), 128, 0, stream>>>(fa, batch);
         EYOC_LAUNCH_CHECK();
-        seed_fitness_kernel<<<dim3((S + FS - 1) / FS, batch), 256, 0, stream>>>(fa);
+        if (g_sc2_reference_kernels & 2) seed_fitness_shared_kernel<<<dim3((S + 7) / 8, batch), 256, 0, stream>>>(fa);
+        else seed_fitness_kernel<<<dim3((S + FS - 1) / FS, batch), 256, 0, stream>>>(fa);
         EYOC_LAUNCH_CHECK();
     }
     RefineArgs ra{P, seed_trans, fitness ? fitness : scores, skip_seed_stage ? hooks->initial_trans : nullptr, n, S,
@@ -1745,5 +1827,10 @@ extern "C" int eyoc_power_iteration_dense(const float* M, int batch, int n, int 
 
 extern "C" int eyoc_debug_sc2_power_fused(int on) {
     g_power_fused = on ? 1 : 0;
+    return EYOC_OK;
+}
+
+extern "C" int eyoc_debug_sc2_reference_kernels(int mask) {
+    g_sc2_reference_kernels = mask & 3;
     return EYOC_OK;
 }

@@ -266,6 +266,9 @@ int eyoc_sparse_conv_h(const void* in0, int c0, const void* in1, int c1, const i
  * 8 CTAs; 0 = one launch per iteration (the path taken anyway when n is too large for the cluster's shared memory).  Both
  * return the same bits. */
 int eyoc_debug_sc2_power_fused(int on);
+/* Test aid of eyoc_sc2pcr: run the kernels that csr_fill_kernel (bit 0) and seed_fitness_kernel (bit 1) replaced; the results must
+ * not change by a bit. */
+int eyoc_debug_sc2_reference_kernels(int mask);
 /* Test aid: cap gridDim.x of the persistent grid (0 = one CTA per SM), so that small inputs walk many tile pairs per CTA. */
 int eyoc_debug_convh_grid_cap(int max_ctas);
 /* Tuning aid: 1 = one MMA-issuing thread in the 128-channel instantiation (default), 2 = one per accumulator tile. */

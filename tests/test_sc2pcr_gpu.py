@@ -252,3 +252,50 @@ def test_power_iteration_cluster_kernel_matches_stepwise(n, inlier_frac, batch):
     assert bool(torch.isfinite(res[1][0]).all()) and float(res[1][0].abs().max()) > 0
     for a, b in zip(res[0], res[1]):
         assert torch.equal(a, b)
+
+
+def test_replaced_kernels_equal_their_references():
+    """csr_fill_kernel (two passes) and seed_fitness_kernel (transforms in registers) against the kernels they replaced
+    (eyoc_debug_sc2_reference_kernels), bit for bit: confidence, fitness, pose, labels - on random correspondence sets (sparse,
+    dense) and on a block of pipeline pairs at the KITTI configuration (close and distant)."""
+    from eyoc_b200 import _C, synth
+    from eyoc_b200.model import load_model
+    from eyoc_b200.pipeline import RegistrationPipeline
+    from eyoc_b200.scripts.SC2_PCR.SC2_PCR import Matcher
+    from oracle import resunet_oracle as RO
+    lib = _C.lib()
+    m = Matcher(inlier_threshold=0.6, num_node='all', use_mutual=False, d_thre=0.1, num_iterations=20, ratio=0.2,
+                nms_radius=0.6, max_points=8000, k1=30, k2=20)
+    cases = []
+    for n, frac, batch in ((8000, 0.15, 3), (3000, 0.6, 2), (700, 1.0, 2)):
+        rng = np.random.default_rng(n)
+        src = rng.uniform(-40, 40, (batch, n, 3)).astype(np.float32)
+        tgt = src + np.float32([1.0, -2.0, 0.5]) + rng.normal(0, 0.02, src.shape).astype(np.float32)
+        out = rng.random((batch, n)) >= frac
+        tgt[out] = rng.uniform(-40, 40, (int(out.sum()), 3)).astype(np.float32)
+        cases.append((torch.from_numpy(src).cuda(), torch.from_numpy(tgt).cuda()))
+    model = load_model('ResUNetBN2C')(1, 32, bn_momentum=0.05, normalize_feature=True, conv1_kernel_size=5, D=3)
+    model.load_state_dict(RO.make_state_dict(1, 32, 5, seed=2))
+    pipe = RegistrationPipeline(model.cuda().eval(), Matcher(inlier_threshold=0.6, num_node=8000, use_mutual=False, d_thre=0.1,
+                                                             num_iterations=20, ratio=0.2, nms_radius=0.6, max_points=8000, k1=30, k2=20))
+    pairs = synth.make_pairs([1064, 1065, 1066, 1067, 1068, 1069])
+    coords, xyz, desc, sizes = synth.collate_pairs(pairs)
+    cd, xd, dd = torch.from_numpy(coords).cuda(), torch.from_numpy(xyz).cuda(), torch.from_numpy(desc).cuda()
+    res = {}
+    try:
+        for mask in (0, 1, 2, 3):
+            assert lib.eyoc_debug_sc2_reference_kernels(mask) == 0
+            got = []
+            for s, t in cases:
+                det = {}
+                T, fit, labels = m._run(s, t, want_labels=True, detail=det)
+                got += [det['confidence'].clone(), fit.clone(), T.clone(), labels.clone()]
+            np.random.seed(64)
+            o = pipe.run(cd, xd, sizes, descriptors=dd)
+            got += [o['trans'].clone(), o['labels'].clone(), o['fitness'].clone()]
+            res[mask] = got
+    finally:
+        lib.eyoc_debug_sc2_reference_kernels(0)
+    for mask in (1, 2, 3):
+        for i, (a, b) in enumerate(zip(res[0], res[mask])):
+            assert torch.equal(a, b), (mask, i)

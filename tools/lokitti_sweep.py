@@ -35,6 +35,7 @@ def main():
     ap.add_argument('--block', type=int, default=64)
     ap.add_argument('--oracle-pairs', type=int, default=6)
     ap.add_argument('--out', default=None)
+    ap.add_argument('--dump', default=None, help='write the gathered record table (.npy)')
     args = ap.parse_args()
     import torch.distributed as dist
     from eyoc_b200.pipeline import gather_records, shard_range
@@ -42,6 +43,9 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    if os.environ.get('EYOC_SWEEP_POWER_STEPWISE'):       # diagnostic: the per-iteration power-iteration kernel
+        from eyoc_b200 import _C
+        _C.lib().eyoc_debug_sc2_power_fused(0)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     cfg = tk.make_config(tk.parse_args(['--use_RANSAC', 'false']))
@@ -85,6 +89,8 @@ def main():
     if rank != 0:
         dist.destroy_process_group()
         return
+    if args.dump:
+        np.save(args.dump, table_all)
     for r in table_all:
         T = r[:16].reshape(4, 4)
         rte = float(np.linalg.norm(T[:3, 3] - r[20:23]))
