@@ -475,7 +475,9 @@ def run_ours(args):
         rres.append(np.degrees(rre))
         succ += is_success(rte, rre)
     line = {'metric': 'point-cloud pairs/sec', 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': K, 'warmup': W,
-            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': {'f16x3': 'f32 (conv operands as fp16 hi/lo pairs: 22 significant bits, fp32 accumulation)',
+                      'tf32x3': 'f32 (conv operands as tf32 hi/lo pairs, fp32 accumulation)'}.get(enn.CONV_MODE, 'f32'),
             'data': 'synthetic KITTI-shaped LiDAR pairs (ray-cast generator, seeded); random-init weights'
                     + ('; estimator fed planted descriptors (the forward pass still runs and is timed)' if desc_d is not None else ''),
             'config': {'workload': workload_name(args.model), 'pairs_per_gpu': P, 'global_pairs': P * world, 'voxels_per_step_per_gpu': int(coords_np.shape[0]),
